@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""Benchmark of the log-mel hot path (BASELINE.json metric: log-mel audio-seconds/second).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c2|c3]
+
+One "step" = one pass of the hot path over one batch of synthetic PCM.  Default workload is
+BASELINE.json configs[1] (whisper-small 80-mel, batch 256 x 30 s, device-resident PCM, one
+B200).  With N > 1 (launched by torchrun, one rank per GPU) every rank processes its own batch
+of the same size -- the path shards by clip with no data-path collective -- so scaling is WEAK
+and `value` is the whole-job audio-seconds/second.  `--workload c3` is BASELINE configs[2]
+(large-v3 128-mel, 1024 clips split across the ranks: strong scaling).
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for how every field is derived.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_SAMPLES = 480000
+N_FRAMES = 3000
+CLIP_SECONDS = 30.0
+
+WORKLOADS = {
+    # name: (n_mels, clips per GPU at N=1, strong?)
+    "c2": dict(n_mels=80, batch=256, strong=False,
+               label="C2: whisper-small 80-mel, batch 256 x 30 s f32 PCM per GPU (BASELINE configs[1])"),
+    "c3": dict(n_mels=128, batch=1024, strong=True,
+               label="C3: whisper-large-v3 128-mel, 1024 x 30 s sharded by clip (BASELINE configs[2])"),
+}
+
+
+def algorithmic_bytes_per_clip(n_mels: int) -> int:
+    # read 480000*4 B PCM + write n_mels*3000*4 B features
+    return N_SAMPLES * 4 + n_mels * N_FRAMES * 4
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            d = json.load(open(path))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons of one GPU through NVML while the timed region runs."""
+
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index: int, period_s: float = 0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period_s
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_ev = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        while not self._stop_ev.is_set():
+            try:
+                self.samples.append(int(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+                mask = int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                for bit, name in self.REASONS.items():
+                    if mask & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_ev.set()
+        if self.ok:
+            self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def visible_nvml_index(local_rank: int) -> int:
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except Exception:
+            return local_rank
+    return local_rank
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU implementation (HF WhisperFeatureExtractor through a
+# DataLoader shaped like REF/data_utils/data_loader.py:170-172 + data_collator.py:64-76)
+# ------------------------------------------------------------------------------------------------
+def synth_noise_clips(n, seed):
+    import numpy as np
+
+    rng = np.random.default_rng(seed)
+    return [(0.1 * rng.standard_normal(N_SAMPLES)).astype(np.float32) for _ in range(n)]
+
+
+def run_reference(args, wl, rank, world):
+    if rank != 0:
+        return
+    from oracle.hf_reference import time_reference_dataloader
+
+    cores = len(os.sched_getaffinity(0))
+    # bounded sample: ~cores * 12 clips per step keeps a step to a few seconds of host time
+    clips_per_step = max(16, min(wl["batch"], cores * 12))
+    clips_per_step = (clips_per_step + 15) // 16 * 16
+    clips = synth_noise_clips(min(clips_per_step, 64), seed=1)
+    clips = [clips[i % len(clips)] for i in range(clips_per_step)]
+    for _ in range(args.warmup):
+        time_reference_dataloader(clips[: max(16, cores * 2)], wl["n_mels"], 16, cores, "default", warmup_batches=0)
+    t_total, n_total = 0.0, 0
+    for _ in range(args.steps):
+        r = time_reference_dataloader(clips, wl["n_mels"], 16, cores, "default", warmup_batches=0)
+        t_total += r["seconds"]
+        n_total += r["clips"]
+    value = CLIP_SECONDS * n_total / t_total
+    sample = (f"{clips_per_step} x 30 s white-noise clips per step through a torch DataLoader "
+              f"(batch 16, {cores} workers, 1 torch thread each) running the unmodified "
+              f"transformers WhisperFeatureExtractor per clip + feature_extractor.pad stack")
+    line = {
+        "impl": "reference", "metric": "log-mel audio-seconds/second", "value": value, "unit": "audio-s/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t_total / max(1, args.steps), "higher_is_better": True,
+        "scaling": "strong" if wl["strong"] else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["label"], "n_mels": wl["n_mels"], "sample_clips_per_step": clips_per_step},
+        "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, wl, rank, world, local_rank):
+    import torch
+
+    import whisper_context_biasing_b200 as W
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        dist.init_process_group(backend="nccl", device_id=dev)
+
+    n_mels = wl["n_mels"]
+    B = wl["batch"] // world if wl["strong"] else wl["batch"]
+    fe = W.B200WhisperFeatureExtractor(feature_size=n_mels, device=dev)
+
+    # synthetic PCM (family F1, white Gaussian sigma 0.1), generated on the host, pinned
+    g = torch.Generator(device="cpu").manual_seed(1000 + rank)
+    host_pcm = torch.empty((B, N_SAMPLES), dtype=torch.float32).pin_memory()
+    torch.randn((B, N_SAMPLES), generator=g, out=host_pcm)
+    host_pcm.mul_(0.1)
+    pcm = host_pcm.to(dev, non_blocking=True)
+    out = torch.empty((B, n_mels, N_FRAMES), dtype=torch.float32, device=dev)
+    torch.cuda.synchronize(dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident: PCM already in HBM -------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        fe.extract_device(pcm, out=out)
+    barrier()
+    sampler = ClockSampler(visible_nvml_index(local_rank))
+    sampler.start()
+    launches0 = fe.launch_count
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for s in range(args.steps):
+        evs[s][0].record()
+        fe.extract_device(pcm, out=out)
+        evs[s][1].record()
+    t1.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = fe.launch_count - launches0
+    dev_ms = t0.elapsed_time(t1)
+    launch_ms = sum(a.elapsed_time(b) for a, b in evs) / args.steps
+
+    # ---- end to end: pinned host PCM -> H2D -> kernels -> D2H of the per-clip max --------------
+    gmax_host = torch.empty((B,), dtype=torch.float32).pin_memory()
+    clips = [host_pcm[b].numpy() for b in range(B)]
+    e2e_steps = max(2, min(args.steps, 5))
+
+    def e2e_step():
+        fe.extract_host(clips, out=out)
+        gmax_host.copy_(out[:, 0, 0], non_blocking=True)      # D2H read of the step's result
+        torch.cuda.current_stream(dev).synchronize()
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    w0 = time.perf_counter()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    e2e_ms = max(e0.elapsed_time(e1), 0.0)
+    e2e_wall_ms = 1e3 * (time.perf_counter() - w0)
+    e2e_ms = max(e2e_ms, 0.0)
+
+    # ---- max over ranks ----------------------------------------------------------------------
+    if dist is not None:
+        t = torch.tensor([dev_ms, e2e_ms, launch_ms, e2e_wall_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_ms, launch_ms, e2e_wall_ms = [float(v) for v in t.tolist()]
+
+    total_clips = B * world
+    value = CLIP_SECONDS * total_clips * args.steps / (dev_ms * 1e-3)
+    e2e_value = CLIP_SECONDS * total_clips * e2e_steps / (e2e_ms * 1e-3)
+    peak, peak_src = measured_peaks()
+    alg_bytes = algorithmic_bytes_per_clip(n_mels) * B
+    achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
+
+    if rank == 0:
+        line = {
+            "metric": "log-mel audio-seconds/second", "value": value, "unit": "audio-s/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong" if wl["strong"] else "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["label"], "n_mels": n_mels, "clips_per_gpu": B, "clip_seconds": 30,
+                       "l2_policy": f"inputs larger than L2: {B * N_SAMPLES * 4 / 1e6:.0f} MB PCM + "
+                                    f"{B * n_mels * N_FRAMES * 4 / 1e6:.0f} MB features per step",
+                       "timing": "CUDA events on the launch stream, barrier + synchronize both sides, max over ranks"},
+            "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": B * N_SAMPLES * 4 + B * 12,
+                    "d2h_bytes_per_step": B * 4, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
+                    "wall_ms_per_step": e2e_wall_ms / e2e_steps,
+                    "what": "wlm_logmel_host: pinned host f32 PCM -> chunked H2D overlapped with the kernels -> "
+                            "features stay in HBM; D2H of one float per clip"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": KERNEL_DRAM_TRAFFIC_BYTES.get(n_mels),
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                         "launch_ms": launch_ms},
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline and world >= 1:
+            line["cpu_baseline"] = cpu_baseline(n_mels)
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel for one launch of the
+# default workload, from the `ncu --set full` capture summarised under profiles/ (None = not
+# captured yet for this kernel version).
+KERNEL_DRAM_TRAFFIC_BYTES = {80: None, 128: None}
+
+
+def cpu_baseline(n_mels):
+    """The reference's CPU implementation on this box's host cores, bounded sample (~10-30 s)."""
+    from oracle.hf_reference import time_reference_dataloader
+
+    cores = len(os.sched_getaffinity(0))
+    n = max(32, min(cores * 16, 512))
+    n = (n + 15) // 16 * 16
+    base = synth_noise_clips(min(n, 32), seed=1)
+    clips = [base[i % len(base)] for i in range(n)]
+    r = time_reference_dataloader(clips, n_mels, 16, cores, "default", warmup_batches=1)
+    return {"value": r["audio_s_per_s"], "unit": "audio-s/s", "cores": cores, "kind": "reference",
+            "sample": f"{r['clips']} x 30 s white-noise clips, torch DataLoader batch 16, {cores} workers x 1 thread, "
+                      f"unmodified transformers WhisperFeatureExtractor per clip + pad stack ({r['seconds']:.1f} s)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl, rank, world)
+        return
+    if world == 1 and args.gpus > 1:
+        print(f"bench.py: --gpus {args.gpus} needs torchrun (one rank per GPU); running rank 0 only", file=sys.stderr)
+    run_ours(args, wl, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,496 @@
+// libwlm.so -- C ABI (include/wlm.h) over the sm_100a log-mel kernels.
+//
+// Host side only: plan construction (mel table -> sparse form, constant tables), argument
+// validation, launch sequencing, the pinned-ring H2D pipeline of wlm_logmel_host.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#ifdef WLM_HAVE_FUSED
+#include "logmel_fused.cuh"
+#endif
+#include "logmel_v0.cuh"
+#include "wlm_common.cuh"
+
+using namespace wlm;
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define WLM_CUDA(expr)                                                                      \
+    do {                                                                                    \
+        cudaError_t e_ = (expr);                                                            \
+        if (e_ != cudaSuccess)                                                              \
+            return fail(WLM_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                                \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------
+struct wlm_plan {
+    int device = -1;
+    int n_mels = 0;
+    int sm_count = 0;
+#ifdef WLM_HAVE_FUSED
+    int impl = 1;  // 1 = fused cluster kernel (product); 0 = v0 bring-up path (WLM_IMPL=v0, debug)
+#else
+    int impl = 0;
+#endif
+    std::atomic<int64_t> launches{0};
+
+    // constant tables (device)
+    float2* d_tw = nullptr;        // [400] (cos, -sin)
+    float* d_win = nullptr;        // [400]
+    float* d_mel_dense = nullptr;  // [n_mels][201]
+    int16_t* d_klo = nullptr;      // [n_mels]
+    int16_t* d_khi = nullptr;      // [n_mels]
+    MelSparse* d_sparse = nullptr;
+    MelSparse h_sparse;
+#ifdef WLM_HAVE_FUSED
+    fused::Tables* d_fused_tables = nullptr;
+#endif
+    int max_clusters = 0;          // co-resident clusters of the fused kernel (occupancy query)
+
+    // wlm_logmel_host pipeline
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_chunk[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_slot_free[2] = {nullptr, nullptr};
+    cudaEvent_t ev_kernels_done = nullptr;
+    bool kernels_done_valid = false;
+    void* d_stage = nullptr;  // packed PCM
+    size_t d_stage_bytes = 0;
+    void* h_ring[2] = {nullptr, nullptr};
+    size_t h_ring_bytes = 0;
+    int64_t* d_offsets = nullptr;
+    int32_t* d_lengths = nullptr;
+    int64_t* h_offsets = nullptr;  // pinned
+    int32_t* h_lengths = nullptr;  // pinned
+    int meta_cap = 0;
+    void* d_ws = nullptr;
+    size_t d_ws_bytes = 0;
+};
+
+extern "C" int wlm_version(void) { return WLM_VERSION; }
+extern "C" const char* wlm_last_error(void) { return g_last_error.c_str(); }
+
+static int build_sparse(const float* dense, int n_mels, MelSparse* sp, std::vector<int16_t>* klo,
+                        std::vector<int16_t>* khi) {
+    klo->assign(n_mels, 0);
+    khi->assign(n_mels, -1);
+    std::vector<int> seen(n_mels, 0);
+    memset(sp, 0, sizeof(*sp));
+    for (int k = 0; k < kNFreq + 3; ++k) sp->lo[k] = -1;  // -1 = "filter before the first" (dummy)
+    int prev_lo = -1;
+    for (int k = 0; k < kNFreq; ++k) {
+        int idx[3], n = 0;
+        for (int m = 0; m < n_mels; ++m) {
+            const float w = dense[k * n_mels + m];
+            if (!(w == w) || std::isinf(w)) return fail(WLM_ERR_BAD_ARG, "mel table has a non-finite entry at [%d][%d]", k, m);
+            if (w != 0.0f) {
+                if (n == 2) return fail(WLM_ERR_UNSUPPORTED, "mel table: FFT bin %d feeds more than two filters", k);
+                idx[n++] = m;
+                if (!seen[m]) { (*klo)[m] = (int16_t)k; seen[m] = 1; }
+                if ((*khi)[m] >= 0 && (*khi)[m] != k - 1)
+                    return fail(WLM_ERR_UNSUPPORTED, "mel table: filter %d has non-contiguous support at bin %d", m, k);
+                (*khi)[m] = (int16_t)k;
+            }
+        }
+        if (n == 2 && idx[1] != idx[0] + 1)
+            return fail(WLM_ERR_UNSUPPORTED, "mel table: FFT bin %d feeds non-adjacent filters %d,%d", k, idx[0], idx[1]);
+        if (n == 0) {
+            sp->lo[k] = (int16_t)prev_lo;  // both weights 0
+        } else if (n == 2) {
+            sp->lo[k] = (int16_t)idx[0];
+            sp->w_lo[k] = dense[k * n_mels + idx[0]];
+            sp->w_hi[k] = dense[k * n_mels + idx[1]];
+        } else if (idx[0] == prev_lo + 1) {
+            // single filter, and it is the upper one of the running pair (first interval, a bin
+            // exactly on a filter centre, last interval): keep the pair, weight goes to "hi"
+            sp->lo[k] = (int16_t)prev_lo;
+            sp->w_hi[k] = dense[k * n_mels + idx[0]];
+        } else {
+            sp->lo[k] = (int16_t)idx[0];
+            sp->w_lo[k] = dense[k * n_mels + idx[0]];
+        }
+        if (sp->lo[k] < prev_lo) return fail(WLM_ERR_UNSUPPORTED, "mel table: filter order not monotone at bin %d", k);
+        prev_lo = sp->lo[k];
+    }
+    for (int m = 0; m < n_mels; ++m)
+        if (!seen[m]) { (*klo)[m] = 0; (*khi)[m] = -1; }  // empty filter: contributes 0 -> log10(1e-10)
+    return WLM_OK;
+}
+
+extern "C" int wlm_plan_create(int device, int n_mels, const float* mel_dense_host, wlm_plan** out) {
+    if (!out) return fail(WLM_ERR_BAD_ARG, "out is NULL");
+    *out = nullptr;
+    if (!mel_dense_host) return fail(WLM_ERR_BAD_ARG, "mel_dense_host is NULL");
+    if (n_mels < 1 || n_mels > kMaxMels) return fail(WLM_ERR_UNSUPPORTED, "n_mels=%d outside [1,%d]", n_mels, kMaxMels);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(WLM_ERR_NO_DEVICE, "no CUDA device (%s); libwlm has no CPU fallback", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(WLM_ERR_BAD_ARG, "device %d out of range [0,%d)", device, ndev);
+    cudaDeviceProp prop;
+    WLM_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(WLM_ERR_NO_DEVICE, "device %d is sm_%d%d; libwlm is built for sm_100a only", device, prop.major, prop.minor);
+    WLM_CUDA(cudaSetDevice(device));
+
+    wlm_plan* p = new wlm_plan();
+    p->device = device;
+    p->n_mels = n_mels;
+    p->sm_count = prop.multiProcessorCount;
+    const char* impl_env = getenv("WLM_IMPL");
+    if (impl_env && strcmp(impl_env, "v0") == 0) p->impl = 0;
+
+    std::vector<int16_t> klo, khi;
+    int rc = build_sparse(mel_dense_host, n_mels, &p->h_sparse, &klo, &khi);
+    if (rc != WLM_OK) { delete p; return rc; }
+
+    std::vector<float2> tw(kNfft);
+    std::vector<float> win(kNfft);
+    for (int j = 0; j < kNfft; ++j) {
+        const double ang = 2.0 * M_PI * j / kNfft;
+        tw[j] = make_float2((float)cos(ang), (float)-sin(ang));
+        win[j] = (float)(0.5 - 0.5 * cos(ang));  // periodic Hann, TF-FE:141
+    }
+    std::vector<float> melT((size_t)n_mels * kNFreq);
+    for (int k = 0; k < kNFreq; ++k)
+        for (int m = 0; m < n_mels; ++m) melT[(size_t)m * kNFreq + k] = mel_dense_host[k * n_mels + m];
+
+#define WLM_CUDA_P(expr)                                                                          \
+    do {                                                                                          \
+        cudaError_t e_ = (expr);                                                                  \
+        if (e_ != cudaSuccess) {                                                                  \
+            wlm_plan_destroy(p);                                                                  \
+            return fail(WLM_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+        }                                                                                         \
+    } while (0)
+
+    WLM_CUDA_P(cudaMalloc(&p->d_tw, sizeof(float2) * kNfft));
+    WLM_CUDA_P(cudaMalloc(&p->d_win, sizeof(float) * kNfft));
+    WLM_CUDA_P(cudaMalloc(&p->d_mel_dense, sizeof(float) * melT.size()));
+    WLM_CUDA_P(cudaMalloc(&p->d_klo, sizeof(int16_t) * n_mels));
+    WLM_CUDA_P(cudaMalloc(&p->d_khi, sizeof(int16_t) * n_mels));
+    WLM_CUDA_P(cudaMalloc(&p->d_sparse, sizeof(MelSparse)));
+    WLM_CUDA_P(cudaMemcpy(p->d_tw, tw.data(), sizeof(float2) * kNfft, cudaMemcpyHostToDevice));
+    WLM_CUDA_P(cudaMemcpy(p->d_win, win.data(), sizeof(float) * kNfft, cudaMemcpyHostToDevice));
+    WLM_CUDA_P(cudaMemcpy(p->d_mel_dense, melT.data(), sizeof(float) * melT.size(), cudaMemcpyHostToDevice));
+    WLM_CUDA_P(cudaMemcpy(p->d_klo, klo.data(), sizeof(int16_t) * n_mels, cudaMemcpyHostToDevice));
+    WLM_CUDA_P(cudaMemcpy(p->d_khi, khi.data(), sizeof(int16_t) * n_mels, cudaMemcpyHostToDevice));
+    WLM_CUDA_P(cudaMemcpy(p->d_sparse, &p->h_sparse, sizeof(MelSparse), cudaMemcpyHostToDevice));
+
+#ifdef WLM_HAVE_FUSED
+    {
+        fused::Tables ht;
+        fused::build_tables(p->h_sparse, n_mels, &ht);
+        WLM_CUDA_P(cudaMalloc(&p->d_fused_tables, sizeof(fused::Tables)));
+        WLM_CUDA_P(cudaMemcpy(p->d_fused_tables, &ht, sizeof(ht), cudaMemcpyHostToDevice));
+        cudaError_t fe = fused::configure(n_mels, &p->max_clusters);
+        if (fe != cudaSuccess) {
+            wlm_plan_destroy(p);
+            return fail(WLM_ERR_CUDA, "fused kernel configuration failed: %s", cudaGetErrorString(fe));
+        }
+    }
+#endif
+
+    WLM_CUDA_P(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
+    for (auto& ev : p->ev_chunk) WLM_CUDA_P(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    for (auto& ev : p->ev_slot_free) WLM_CUDA_P(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    WLM_CUDA_P(cudaEventCreateWithFlags(&p->ev_kernels_done, cudaEventDisableTiming));
+#undef WLM_CUDA_P
+    *out = p;
+    return WLM_OK;
+}
+
+extern "C" int wlm_plan_destroy(wlm_plan* p) {
+    if (!p) return WLM_OK;
+    cudaSetDevice(p->device);
+    cudaDeviceSynchronize();
+    cudaFree(p->d_tw); cudaFree(p->d_win); cudaFree(p->d_mel_dense); cudaFree(p->d_klo); cudaFree(p->d_khi);
+    cudaFree(p->d_sparse);
+#ifdef WLM_HAVE_FUSED
+    cudaFree(p->d_fused_tables);
+#endif
+    cudaFree(p->d_stage); cudaFree(p->d_offsets); cudaFree(p->d_lengths); cudaFree(p->d_ws);
+    for (auto& r : p->h_ring) if (r) cudaFreeHost(r);
+    if (p->h_offsets) cudaFreeHost(p->h_offsets);
+    if (p->h_lengths) cudaFreeHost(p->h_lengths);
+    for (auto& ev : p->ev_chunk) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : p->ev_slot_free) if (ev) cudaEventDestroy(ev);
+    if (p->ev_kernels_done) cudaEventDestroy(p->ev_kernels_done);
+    if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
+    delete p;
+    return WLM_OK;
+}
+
+extern "C" int wlm_plan_n_mels(const wlm_plan* p) { return p ? p->n_mels : fail(WLM_ERR_BAD_ARG, "plan is NULL"); }
+extern "C" int wlm_plan_device(const wlm_plan* p) { return p ? p->device : fail(WLM_ERR_BAD_ARG, "plan is NULL"); }
+extern "C" int wlm_plan_sm_count(const wlm_plan* p) { return p ? p->sm_count : fail(WLM_ERR_BAD_ARG, "plan is NULL"); }
+extern "C" int64_t wlm_plan_launch_count(const wlm_plan* p) { return p ? p->launches.load() : -1; }
+
+extern "C" size_t wlm_workspace_bytes(const wlm_plan* p, int B) {
+    if (!p || B <= 0) return 0;
+    return ((size_t)B * sizeof(float) + 255) / 256 * 256;  // per-clip gmax when the caller passes none
+}
+
+// ------------------------------------------------------------------------------------------
+// launch
+// ------------------------------------------------------------------------------------------
+static int launch_logmel(wlm_plan* p, const ClipArgs& a, cudaStream_t st) {
+    if (p->impl == 0) {
+        v0::init_gmax<<<(a.B + 255) / 256, 256, 0, st>>>(a.gmax, a.B);
+        dim3 grid((kNFrames + v0::kFramesPerCta - 1) / v0::kFramesPerCta, a.B);
+        v0::logmel_k1<<<grid, v0::kThreads, 0, st>>>(a, p->d_tw, p->d_win, p->d_mel_dense, p->d_klo, p->d_khi);
+        const int64_t total4 = (int64_t)a.B * a.n_mels * kNFrames / 4;
+        int blocks = (int)std::min<int64_t>((total4 + 255) / 256, (int64_t)p->sm_count * 16);
+        v0::logmel_k2<<<blocks, 256, 0, st>>>(a.out, a.gmax, a.n_mels, a.B);
+        p->launches += 3;
+    }
+#ifdef WLM_HAVE_FUSED
+    else {
+        cudaError_t e = fused::launch(a, p->d_fused_tables, p->sm_count, p->max_clusters, st);
+        if (e != cudaSuccess) return fail(WLM_ERR_CUDA, "fused launch failed: %s", cudaGetErrorString(e));
+        p->launches += 1;
+    }
+#endif
+    WLM_CUDA(cudaGetLastError());
+    return WLM_OK;
+}
+
+extern "C" int wlm_logmel(wlm_plan* p, const void* pcm_dev, int pcm_format, const int64_t* offsets_dev,
+                          const int32_t* lengths_dev, int64_t row_stride, int B, float* out_dev,
+                          float* gmax_dev, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!p) return fail(WLM_ERR_BAD_ARG, "plan is NULL");
+    if (B < 0) return fail(WLM_ERR_BAD_ARG, "B=%d is negative", B);
+    if (B == 0) return WLM_OK;
+    if (!pcm_dev || !out_dev) return fail(WLM_ERR_BAD_ARG, "pcm_dev/out_dev is NULL");
+    if (pcm_format != WLM_PCM_F32 && pcm_format != WLM_PCM_I16) return fail(WLM_ERR_BAD_ARG, "unknown pcm_format %d", pcm_format);
+    if ((reinterpret_cast<uintptr_t>(pcm_dev) & 15) || (reinterpret_cast<uintptr_t>(out_dev) & 15))
+        return fail(WLM_ERR_BAD_ARG, "pcm_dev and out_dev must be 16-byte aligned");
+    if (!offsets_dev) {
+        if (row_stride <= 0) return fail(WLM_ERR_BAD_ARG, "dense layout needs row_stride > 0 (got %lld)", (long long)row_stride);
+        if (row_stride % 4) return fail(WLM_ERR_BAD_ARG, "dense row_stride must be a multiple of 4 elements (got %lld)", (long long)row_stride);
+    } else if (!lengths_dev) {
+        return fail(WLM_ERR_BAD_ARG, "ragged layout (offsets_dev) needs lengths_dev");
+    }
+    float* gmax = gmax_dev;
+    if (!gmax) {
+        const size_t need = wlm_workspace_bytes(p, B);
+        if (!workspace || workspace_bytes < need)
+            return fail(WLM_ERR_WORKSPACE, "workspace %zu B < required %zu B", workspace_bytes, need);
+        gmax = static_cast<float*>(workspace);
+    }
+    WLM_CUDA(cudaSetDevice(p->device));
+    ClipArgs a;
+    a.pcm = pcm_dev;
+    a.offsets = offsets_dev;
+    a.lengths = lengths_dev;
+    a.row_stride = row_stride;
+    a.dense_len = (int32_t)std::min<int64_t>(row_stride > 0 ? row_stride : 0, kNSamples);
+    a.pcm_format = pcm_format;
+    a.n_mels = p->n_mels;
+    a.B = B;
+    a.out = out_dev;
+    a.gmax = gmax;
+    return launch_logmel(p, a, static_cast<cudaStream_t>(stream));
+}
+
+// ------------------------------------------------------------------------------------------
+// attention mask (TF-FE:328-337)
+// ------------------------------------------------------------------------------------------
+__global__ void frame_mask_kernel(const int32_t* __restrict__ lengths, int B, int32_t* __restrict__ mask) {
+    const int64_t total = (int64_t)B * kNFrames;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int b = (int)(i / kNFrames), t = (int)(i - (int64_t)b * kNFrames);
+        const int len = max(0, min(lengths[b], kNSamples));
+        mask[i] = (t * kHop < len) ? 1 : 0;
+    }
+}
+
+extern "C" int wlm_frame_mask(wlm_plan* p, const int32_t* lengths_dev, int B, int32_t* mask_dev, void* stream) {
+    if (!p) return fail(WLM_ERR_BAD_ARG, "plan is NULL");
+    if (B < 0) return fail(WLM_ERR_BAD_ARG, "B=%d is negative", B);
+    if (B == 0) return WLM_OK;
+    if (!lengths_dev || !mask_dev) return fail(WLM_ERR_BAD_ARG, "lengths_dev/mask_dev is NULL");
+    WLM_CUDA(cudaSetDevice(p->device));
+    const int64_t total = (int64_t)B * kNFrames;
+    const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)p->sm_count * 8);
+    frame_mask_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(lengths_dev, B, mask_dev);
+    p->launches += 1;
+    WLM_CUDA(cudaGetLastError());
+    return WLM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// host-buffer end-to-end path
+// ------------------------------------------------------------------------------------------
+static bool is_pinned_host(const void* ptr) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost;
+}
+
+extern "C" int wlm_logmel_host(wlm_plan* p, const void* const* clips_host, const int32_t* lengths_host,
+                               int pcm_format, int B, float* out_dev, float* out_host, void* stream) {
+    if (!p) return fail(WLM_ERR_BAD_ARG, "plan is NULL");
+    if (B < 0) return fail(WLM_ERR_BAD_ARG, "B=%d is negative", B);
+    if (B == 0) return WLM_OK;
+    if (!clips_host || !lengths_host || !out_dev) return fail(WLM_ERR_BAD_ARG, "clips_host/lengths_host/out_dev is NULL");
+    if (pcm_format != WLM_PCM_F32 && pcm_format != WLM_PCM_I16) return fail(WLM_ERR_BAD_ARG, "unknown pcm_format %d", pcm_format);
+    if (reinterpret_cast<uintptr_t>(out_dev) & 15) return fail(WLM_ERR_BAD_ARG, "out_dev must be 16-byte aligned");
+    WLM_CUDA(cudaSetDevice(p->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t esz = pcm_format == WLM_PCM_I16 ? 2 : 4;
+    const int64_t align_el = 16 / esz * 2;  // clip starts at 32-byte boundaries of the packed buffer
+
+    // metadata
+    if (B > p->meta_cap) {
+        cudaFree(p->d_offsets); cudaFree(p->d_lengths);
+        if (p->h_offsets) cudaFreeHost(p->h_offsets);
+        if (p->h_lengths) cudaFreeHost(p->h_lengths);
+        p->d_offsets = nullptr; p->d_lengths = nullptr; p->h_offsets = nullptr; p->h_lengths = nullptr;
+        p->meta_cap = 0;
+        const int cap = std::max(B, 256);
+        WLM_CUDA(cudaMalloc(&p->d_offsets, sizeof(int64_t) * cap));
+        WLM_CUDA(cudaMalloc(&p->d_lengths, sizeof(int32_t) * cap));
+        WLM_CUDA(cudaMallocHost(&p->h_offsets, sizeof(int64_t) * cap));
+        WLM_CUDA(cudaMallocHost(&p->h_lengths, sizeof(int32_t) * cap));
+        p->meta_cap = cap;
+    }
+    // a previous call's kernels may still be reading the staging buffers / metadata
+    if (p->kernels_done_valid) WLM_CUDA(cudaEventSynchronize(p->ev_kernels_done));
+
+    int64_t total_el = 0;
+    for (int b = 0; b < B; ++b) {
+        if (lengths_host[b] < 0) return fail(WLM_ERR_BAD_ARG, "lengths_host[%d]=%d is negative", b, lengths_host[b]);
+        if (lengths_host[b] > 0 && !clips_host[b]) return fail(WLM_ERR_BAD_ARG, "clips_host[%d] is NULL", b);
+        const int32_t len = std::min<int32_t>(lengths_host[b], kNSamples);
+        p->h_offsets[b] = total_el;
+        p->h_lengths[b] = len;
+        total_el += (len + align_el - 1) / align_el * align_el;
+    }
+    const size_t total_bytes = std::max<size_t>((size_t)total_el * esz, 256);
+    if (total_bytes > p->d_stage_bytes) {
+        cudaFree(p->d_stage);
+        p->d_stage = nullptr; p->d_stage_bytes = 0;
+        WLM_CUDA(cudaMalloc(&p->d_stage, total_bytes));
+        p->d_stage_bytes = total_bytes;
+    }
+    const size_t ws_need = wlm_workspace_bytes(p, B);
+    if (ws_need > p->d_ws_bytes) {
+        cudaFree(p->d_ws);
+        p->d_ws = nullptr; p->d_ws_bytes = 0;
+        WLM_CUDA(cudaMalloc(&p->d_ws, ws_need));
+        p->d_ws_bytes = ws_need;
+    }
+    WLM_CUDA(cudaMemcpyAsync(p->d_offsets, p->h_offsets, sizeof(int64_t) * B, cudaMemcpyHostToDevice, p->copy_stream));
+    WLM_CUDA(cudaMemcpyAsync(p->d_lengths, p->h_lengths, sizeof(int32_t) * B, cudaMemcpyHostToDevice, p->copy_stream));
+
+    // chunks of ~48 MB of PCM: copy chunk c+1 while the kernels of chunk c run
+    const size_t kChunkBytes = 48u << 20;
+    const size_t kRingBytes = 64u << 20;
+    int b0 = 0, chunk = 0, slot_uses[2] = {0, 0};
+    while (b0 < B) {
+        int b1 = b0;
+        size_t bytes = 0;
+        while (b1 < B && (b1 == b0 || bytes + (size_t)p->h_lengths[b1] * esz <= kChunkBytes)) {
+            bytes += (size_t)p->h_lengths[b1] * esz;
+            ++b1;
+        }
+        // copy clips [b0,b1): merge host-contiguous pinned runs into single copies
+        int b = b0;
+        while (b < b1) {
+            const int32_t len = p->h_lengths[b];
+            if (len == 0) { ++b; continue; }
+            const char* src = static_cast<const char*>(clips_host[b]);
+            char* dst = static_cast<char*>(p->d_stage) + p->h_offsets[b] * esz;
+            if (is_pinned_host(src)) {
+                size_t run = (size_t)len * esz;
+                int e = b + 1;
+                while (e < b1 && p->h_lengths[e] > 0 &&
+                       static_cast<const char*>(clips_host[e]) == src + run &&
+                       (size_t)(p->h_offsets[e] * esz) == (size_t)(p->h_offsets[b] * esz) + run)
+                { run += (size_t)p->h_lengths[e] * esz; ++e; }
+                WLM_CUDA(cudaMemcpyAsync(dst, src, run, cudaMemcpyHostToDevice, p->copy_stream));
+                b = e;
+            } else {
+                // pageable source: bounce through the pinned ring, as many clips as fit
+                if (!p->h_ring[0]) {
+                    WLM_CUDA(cudaMallocHost(&p->h_ring[0], kRingBytes));
+                    WLM_CUDA(cudaMallocHost(&p->h_ring[1], kRingBytes));
+                    p->h_ring_bytes = kRingBytes;
+                }
+                const int slot = (slot_uses[0] + slot_uses[1]) & 1;
+                if (slot_uses[slot]) WLM_CUDA(cudaEventSynchronize(p->ev_slot_free[slot]));
+                char* ring = static_cast<char*>(p->h_ring[slot]);
+                size_t used = 0;
+                int e = b;
+                const int64_t first_off = p->h_offsets[b];
+                while (e < b1 && !is_pinned_host(clips_host[e] ? clips_host[e] : ring)) {
+                    const size_t rel = (size_t)(p->h_offsets[e] - first_off) * esz;
+                    const size_t nbytes = (size_t)p->h_lengths[e] * esz;
+                    if (rel + nbytes > p->h_ring_bytes) break;
+                    if (nbytes) memcpy(ring + rel, clips_host[e], nbytes);
+                    used = rel + nbytes;
+                    ++e;
+                }
+                if (e == b) return fail(WLM_ERR_BAD_ARG, "clip %d does not fit the staging ring", b);
+                WLM_CUDA(cudaMemcpyAsync(dst, ring, used, cudaMemcpyHostToDevice, p->copy_stream));
+                WLM_CUDA(cudaEventRecord(p->ev_slot_free[slot], p->copy_stream));
+                slot_uses[slot]++;
+                b = e;
+            }
+        }
+        cudaEvent_t ev = p->ev_chunk[chunk & 3];
+        WLM_CUDA(cudaEventRecord(ev, p->copy_stream));
+        WLM_CUDA(cudaStreamWaitEvent(st, ev, 0));
+        ClipArgs a;
+        a.pcm = p->d_stage;
+        a.offsets = p->d_offsets + b0;
+        a.lengths = p->d_lengths + b0;
+        a.row_stride = 0;
+        a.dense_len = 0;
+        a.pcm_format = pcm_format;
+        a.n_mels = p->n_mels;
+        a.B = b1 - b0;
+        a.out = out_dev + (size_t)b0 * p->n_mels * kNFrames;
+        a.gmax = static_cast<float*>(p->d_ws) + b0;
+        int rc = launch_logmel(p, a, st);
+        if (rc != WLM_OK) return rc;
+        b0 = b1;
+        ++chunk;
+    }
+    WLM_CUDA(cudaEventRecord(p->ev_kernels_done, st));
+    p->kernels_done_valid = true;
+    if (out_host) {
+        WLM_CUDA(cudaMemcpyAsync(out_host, out_dev, sizeof(float) * (size_t)B * p->n_mels * kNFrames,
+                                 cudaMemcpyDeviceToHost, st));
+        WLM_CUDA(cudaStreamSynchronize(st));
+    }
+    // host buffers must be reusable on return
+    WLM_CUDA(cudaStreamSynchronize(p->copy_stream));
+    return WLM_OK;
+}
