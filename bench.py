@@ -132,11 +132,9 @@ def run_reference(args, wl, rank, world):
     clips_per_step = (clips_per_step + 15) // 16 * 16
     clips = synth_noise_clips(min(clips_per_step, 64), seed=1)
     clips = [clips[i % len(clips)] for i in range(clips_per_step)]
-    for _ in range(args.warmup):
-        time_reference_dataloader(clips[: max(16, cores * 2)], wl["n_mels"], 16, cores, "default", warmup_batches=0)
     t_total, n_total = 0.0, 0
-    for _ in range(args.steps):
-        r = time_reference_dataloader(clips, wl["n_mels"], 16, cores, "default", warmup_batches=0)
+    for _ in range(args.steps):            # every step has its own untimed warm-up epoch inside
+        r = time_reference_dataloader(clips, wl["n_mels"], 16, cores, "default")
         t_total += r["seconds"]
         n_total += r["clips"]
     value = CLIP_SECONDS * n_total / t_total
@@ -297,7 +295,7 @@ def cpu_baseline(n_mels):
     n = (n + 15) // 16 * 16
     base = synth_noise_clips(min(n, 32), seed=1)
     clips = [base[i % len(base)] for i in range(n)]
-    r = time_reference_dataloader(clips, n_mels, 16, cores, "default", warmup_batches=1)
+    r = time_reference_dataloader(clips, n_mels, 16, cores, "default")
     return {"value": r["audio_s_per_s"], "unit": "audio-s/s", "cores": cores, "kind": "reference",
             "sample": f"{r['clips']} x 30 s white-noise clips, torch DataLoader batch 16, {cores} workers x 1 thread, "
                       f"unmodified transformers WhisperFeatureExtractor per clip + pad stack ({r['seconds']:.1f} s)"}

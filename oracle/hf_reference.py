@@ -94,28 +94,48 @@ class _RefStyleCollate:
         return self.fe.pad(inp, padding="longest", return_tensors="pt")
 
 
+class _EpochBatches:
+    """batch_sampler living in the main process: lets the warm-up epoch be short while the timed
+    epoch covers every clip, with the same persistent workers."""
+
+    def __init__(self, n, batch_size):
+        self.n, self.bs, self.limit = n, batch_size, None
+
+    def __iter__(self):
+        n = self.n if self.limit is None else min(self.n, self.limit)
+        for i in range(0, n, self.bs):
+            yield list(range(i, min(i + self.bs, n)))
+
+    def __len__(self):
+        n = self.n if self.limit is None else min(self.n, self.limit)
+        return (n + self.bs - 1) // self.bs
+
+
 def time_reference_dataloader(clips, n_mels: int, batch_size: int = 16, num_workers: int | None = None,
-                              path: str = "default", warmup_batches: int = 1):
+                              path: str = "default"):
     """Returns dict(audio_s_per_s, seconds, clips, cores).  Audio-seconds are NOMINAL 30 s
-    windows per clip (the extractor always pads/trims to 30 s)."""
-    import torch
+    windows per clip (the extractor always pads/trims to 30 s).
+
+    Persistent workers; an untimed short epoch (two batches per worker) pays for worker start-up
+    and extractor construction, then one full epoch is timed from the creation of its iterator,
+    so prefetching cannot hide work from the clock."""
     from torch.utils.data import DataLoader
 
     if num_workers is None:
         num_workers = len(os.sched_getaffinity(0))
-    ds = _RefStyleDataset(clips, n_mels, path)
-    dl = DataLoader(ds, batch_size=batch_size, shuffle=False, num_workers=num_workers,
-                    collate_fn=_RefStyleCollate(n_mels), persistent_workers=False,
+    sampler = _EpochBatches(len(clips), batch_size)
+    dl = DataLoader(_RefStyleDataset(clips, n_mels, path), batch_sampler=sampler, num_workers=num_workers,
+                    collate_fn=_RefStyleCollate(n_mels), persistent_workers=num_workers > 0,
                     prefetch_factor=2 if num_workers > 0 else None)
-    it = iter(dl)
-    n_done = 0
-    for _ in range(warmup_batches):
-        b = next(it)
-        n_done += b["input_features"].shape[0]
+    sampler.limit = 2 * batch_size * max(1, num_workers)
+    for _ in dl:
+        pass
+    sampler.limit = None
     t0 = time.perf_counter()
     n_timed = 0
-    for b in it:
+    for b in dl:
         n_timed += b["input_features"].shape[0]
     dt = time.perf_counter() - t0
+    del dl
     return {"audio_s_per_s": 30.0 * n_timed / dt if dt > 0 else 0.0, "seconds": dt,
             "clips": n_timed, "cores": max(1, num_workers)}

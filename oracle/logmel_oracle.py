@@ -178,6 +178,8 @@ FAMILIES = ("noise", "sine", "chirp", "speech", "int16", "gap", "zeros", "tiny")
 
 def synth_clip(family: str, n: int, seed: int) -> np.ndarray:
     """float32 PCM in [-1, 1], 16 kHz mono, `np.random.default_rng(seed)`."""
+    if n == 0:
+        return np.zeros(0, dtype=np.float32)
     rng = np.random.default_rng(seed)
     t = np.arange(n, dtype=np.float64) / SAMPLING_RATE
     if family == "noise":          # F1 white Gaussian sigma 0.1

@@ -67,6 +67,7 @@ struct wlm_plan {
     MelSparse h_sparse;
 #ifdef WLM_HAVE_FUSED
     fused::Tables* d_fused_tables = nullptr;
+    fused::Tables h_fused_tables;
 #endif
     int max_clusters = 0;          // co-resident clusters of the fused kernel (occupancy query)
 
@@ -201,10 +202,9 @@ extern "C" int wlm_plan_create(int device, int n_mels, const float* mel_dense_ho
 
 #ifdef WLM_HAVE_FUSED
     {
-        fused::Tables ht;
-        fused::build_tables(p->h_sparse, n_mels, &ht);
+        fused::build_tables(p->h_sparse, n_mels, &p->h_fused_tables);
         WLM_CUDA_P(cudaMalloc(&p->d_fused_tables, sizeof(fused::Tables)));
-        WLM_CUDA_P(cudaMemcpy(p->d_fused_tables, &ht, sizeof(ht), cudaMemcpyHostToDevice));
+        WLM_CUDA_P(cudaMemcpy(p->d_fused_tables, &p->h_fused_tables, sizeof(fused::Tables), cudaMemcpyHostToDevice));
         cudaError_t fe = fused::configure(n_mels, &p->max_clusters);
         if (fe != cudaSuccess) {
             wlm_plan_destroy(p);
@@ -268,9 +268,10 @@ static int launch_logmel(wlm_plan* p, const ClipArgs& a, cudaStream_t st) {
     }
 #ifdef WLM_HAVE_FUSED
     else {
-        cudaError_t e = fused::launch(a, p->d_fused_tables, p->sm_count, p->max_clusters, st);
+        int n_launches = 0;
+        cudaError_t e = fused::launch(a, p->d_fused_tables, p->h_fused_tables, p->sm_count, p->max_clusters, st, &n_launches);
         if (e != cudaSuccess) return fail(WLM_ERR_CUDA, "fused launch failed: %s", cudaGetErrorString(e));
-        p->launches += 1;
+        p->launches += n_launches;
     }
 #endif
     WLM_CUDA(cudaGetLastError());
@@ -289,7 +290,9 @@ extern "C" int wlm_logmel(wlm_plan* p, const void* pcm_dev, int pcm_format, cons
         return fail(WLM_ERR_BAD_ARG, "pcm_dev and out_dev must be 16-byte aligned");
     if (!offsets_dev) {
         if (row_stride <= 0) return fail(WLM_ERR_BAD_ARG, "dense layout needs row_stride > 0 (got %lld)", (long long)row_stride);
-        if (row_stride % 4) return fail(WLM_ERR_BAD_ARG, "dense row_stride must be a multiple of 4 elements (got %lld)", (long long)row_stride);
+        const int gran = pcm_format == WLM_PCM_I16 ? 8 : 4;
+        if (row_stride % gran)
+            return fail(WLM_ERR_BAD_ARG, "dense row_stride must be a multiple of %d elements (16 bytes), got %lld", gran, (long long)row_stride);
     } else if (!lengths_dev) {
         return fail(WLM_ERR_BAD_ARG, "ragged layout (offsets_dev) needs lengths_dev");
     }
