@@ -61,68 +61,82 @@ constexpr int kSmemY = kYFloat2 * 8;            // 102,528
 constexpr int kSmemP = kPFloat2 * 8;            // 51,456
 constexpr int kSmemBytes = kSmemRaw + kSmemY + kSmemP + 64;
 
-constexpr int kMaxEntries = 400;
-// Mel projection as per-filter gather lists (host-built from the sparse table; weights bit-identical
-// to the caller's dense table).  Passed by value: lives in the constant bank, read with uniform loads.
-struct MelParams {
-    float2 w2[kMaxEntries];      // (w, w) per (filter, bin) entry, filters in order, bins ascending
-    int16_t k0[kMaxMels];        // first bin of filter m
-    int16_t cnt[kMaxMels];       // number of bins of filter m (0 for an empty filter)
-    int16_t e0[kMaxMels];        // first entry of filter m
-    int16_t warp_m0[kWarps + 1]; // filters [warp_m0[w], warp_m0[w+1]) belong to warp w
+// Everything the kernel reads with warp-uniform indices, passed by value (constant bank).
+//
+// Mel projection in streaming form: FFT bin k adds w_lo[k]*P[k] to filter lo[k] and w_hi[k]*P[k] to
+// filter lo[k]+1 (host-built from the caller's dense table, weights bit-identical).  A warp walks its
+// bin range with two accumulators; shift[k] = lo[k] - lo[k-1] says how many filters complete before
+// bin k is consumed.
+struct KernelTables {
+    float4 w4[kNFreq + 3];          // (w_lo, w_lo, w_hi, w_hi) per bin
+    uint8_t shift[kNFreq + 3];      // filters completed before bin k
+    int16_t warp_m0[kWarps + 1];    // filters [warp_m0[w], warp_m0[w+1]) belong to warp w
+    int16_t warp_kb[kWarps];        // first bin of warp w
+    int16_t warp_ke[kWarps];        // one past the last bin of warp w
+    int16_t warp_cur[kWarps];       // filter fed by w_lo at bin warp_kb[w]  (may be warp_m0[w]-1)
+    // stage 2: per k2 slot, float2 offsets into Y (component) and into P (output bin) per FFT16 output
+    int16_t slot_comp_off[16];      // comp * 32
+    int16_t slot_pbin_off[13][16];  // output_bin(k1, k2) * 32, indexed by cfft16 array position
     int16_t n_mels;
 };
+using MelParams = KernelTables;
 
 // Host-visible tables
 struct Tables {
     float win_lane[16 * 25];     // Hann window at n = (25 n1 + 16 t) mod 400
-    MelParams mel;
+    KernelTables mel;
 };
 
-inline void build_tables(const MelSparse& sp, int n_mels, Tables* t) {
+// returns 0, or -1 if a filter has no bins (not supported by the fused path)
+inline int build_tables(const MelSparse& sp, int n_mels, Tables* t) {
     for (int n1 = 0; n1 < 16; ++n1)
         for (int tt = 0; tt < 25; ++tt) {
             const int n = (25 * n1 + 16 * tt) % 400;
             t->win_lane[n1 * 25 + tt] = (float)(0.5 - 0.5 * cos(2.0 * M_PI * n / 400.0));
         }
-    MelParams& mp = t->mel;
+    KernelTables& mp = t->mel;
     memset(&mp, 0, sizeof(mp));
     mp.n_mels = (int16_t)n_mels;
-    int e = 0;
-    for (int m = 0; m < n_mels; ++m) {
-        mp.e0[m] = (int16_t)e;
-        int first = -1, last = -1;
-        for (int k = 0; k < kNFreq; ++k) {
-            const bool hit = (sp.lo[k] == m && sp.w_lo[k] != 0.0f) || (sp.lo[k] + 1 == m && sp.w_hi[k] != 0.0f);
-            if (hit) { if (first < 0) first = k; last = k; }
-        }
-        if (first < 0) { mp.k0[m] = 0; mp.cnt[m] = 0; continue; }
-        mp.k0[m] = (int16_t)first;
-        mp.cnt[m] = (int16_t)(last - first + 1);
-        for (int k = first; k <= last; ++k) {
-            float w = 0.0f;
-            if (sp.lo[k] == m) w = sp.w_lo[k];
-            else if (sp.lo[k] + 1 == m) w = sp.w_hi[k];
-            mp.w2[e++] = make_float2(w, w);
-        }
+    int klo[kMaxMels], khi[kMaxMels];
+    for (int m = 0; m < n_mels; ++m) { klo[m] = -1; khi[m] = -1; }
+    for (int k = 0; k < kNFreq; ++k) {
+        mp.w4[k] = make_float4(sp.w_lo[k], sp.w_lo[k], sp.w_hi[k], sp.w_hi[k]);
+        mp.shift[k] = (uint8_t)(k == 0 ? 0 : sp.lo[k] - sp.lo[k - 1]);
+        if (sp.w_lo[k] != 0.0f && sp.lo[k] >= 0) { const int m = sp.lo[k]; if (klo[m] < 0) klo[m] = k; khi[m] = k; }
+        if (sp.w_hi[k] != 0.0f && sp.lo[k] + 1 < n_mels) { const int m = sp.lo[k] + 1; if (klo[m] < 0) klo[m] = k; khi[m] = k; }
     }
-    // balance (entries + 3 per filter) over the 16 warps, contiguous filter runs
+    for (int m = 0; m < n_mels; ++m)
+        if (klo[m] < 0) return -1;
+    // contiguous filter runs per warp, balanced on (14 + 4.5 * bins) per filter
     double total = 0;
-    for (int m = 0; m < n_mels; ++m) total += mp.cnt[m] + 3.0;
+    for (int m = 0; m < n_mels; ++m) total += 14.0 + 4.5 * (khi[m] - klo[m] + 1);
     int m = 0;
     double acc = 0;
     for (int w = 0; w < kWarps; ++w) {
         mp.warp_m0[w] = (int16_t)m;
         const double target = total * (w + 1) / kWarps;
-        while (m < n_mels && (acc + 0.5 * (mp.cnt[m] + 3.0) <= target || n_mels - m > (kWarps - 1 - w) * 64)) {
-            acc += mp.cnt[m] + 3.0;
+        while (m < n_mels) {
+            const double c = 14.0 + 4.5 * (khi[m] - klo[m] + 1);
+            if (acc + 0.5 * c > target && n_mels - m <= (kWarps - 1 - w) * kMaxMels) break;
+            acc += c;
             ++m;
         }
     }
     mp.warp_m0[kWarps] = (int16_t)n_mels;
-    if (m < n_mels) {  // leftovers go to the last warp
-        mp.warp_m0[kWarps] = (int16_t)n_mels;
+    if (m < n_mels) return -1;
+    for (int w = 0; w < kWarps; ++w) {
+        const int ma = mp.warp_m0[w], mb = mp.warp_m0[w + 1];
+        if (ma >= mb) { mp.warp_kb[w] = 0; mp.warp_ke[w] = 0; mp.warp_cur[w] = 0; continue; }
+        mp.warp_kb[w] = (int16_t)klo[ma];
+        mp.warp_ke[w] = (int16_t)(khi[mb - 1] + 1);
+        mp.warp_cur[w] = (int16_t)sp.lo[klo[ma]];
     }
+    for (int s2 = 0; s2 < fft::kNumSlots; ++s2) {
+        mp.slot_comp_off[s2] = (int16_t)(fft::kSlotComp[s2] * 32);
+        for (int k1 = 0; k1 < 16; ++k1)
+            mp.slot_pbin_off[s2][fft::fft16_slot_of_k1(k1)] = (int16_t)(fft::output_bin(k1, fft::kSlotK2[s2]) * 32);
+    }
+    return 0;
 }
 
 // ---- PTX helpers -------------------------------------------------------------------------------
@@ -266,43 +280,28 @@ __device__ __forceinline__ void stage1(const float* raw, float2* Y, const float 
 }
 
 // ---- stage 2 ----------------------------------------------------------------------------------
-template <int SLOT>
-__device__ __forceinline__ void stage2(const float2* Y, float2* P, int lane) {
-    constexpr int comp = fft::kSlotComp[SLOT];
-    constexpr int k2 = fft::kSlotK2[SLOT];
-    const float2* yl = Y + comp * 32 + lane;
+// warp = k2 slot (uniform), lane = frame pair.  One code path for all 13 slots: the slot only selects
+// table offsets, so every warp runs the same instructions (the 13-way templated version thrashed the
+// instruction cache: 28 % of issue stalls were "no instruction").
+__device__ __forceinline__ void stage2(const KernelTables& kt, const float2* Y, float2* P, int slot, int lane) {
+    const float2* yl = Y + kt.slot_comp_off[slot] + lane;
     V2 xr[16], xi[16];
 #pragma unroll
-    for (int n1 = 0; n1 < 16; ++n1) {
-        xr[n1].v = yl[n1 * kYStride];
-        if (SLOT == 0) xi[n1] = mk(0.f, 0.f);
-        else xi[n1].v = yl[n1 * kYStride + 32];
+    for (int n1 = 0; n1 < 16; ++n1) xr[n1].v = yl[n1 * kYStride];
+    if (slot != 0) {
+#pragma unroll
+        for (int n1 = 0; n1 < 16; ++n1) xi[n1].v = yl[n1 * kYStride + 32];
+    } else {  // k2 = 0: Y is purely real
+#pragma unroll
+        for (int n1 = 0; n1 < 16; ++n1) xi[n1] = mk(0.f, 0.f);
     }
     fft::cfft16<V2>(xr, xi);
+    float2* pl = P + lane;
 #pragma unroll
-    for (int k1 = 0; k1 < (SLOT == 0 ? 9 : 16); ++k1) {
-        const int idx = fft::fft16_slot_of_k1(k1);
-        const V2 pw = vfma(xr[idx], xr[idx], vmul(xi[idx], xi[idx]));
-        P[fft::output_bin(k1, k2) * 32 + lane] = pw.v;
-    }
-}
-
-__device__ __forceinline__ void stage2_dispatch(int slot, const float2* Y, float2* P, int lane) {
-    switch (slot) {
-        case 0: stage2<0>(Y, P, lane); break;
-        case 1: stage2<1>(Y, P, lane); break;
-        case 2: stage2<2>(Y, P, lane); break;
-        case 3: stage2<3>(Y, P, lane); break;
-        case 4: stage2<4>(Y, P, lane); break;
-        case 5: stage2<5>(Y, P, lane); break;
-        case 6: stage2<6>(Y, P, lane); break;
-        case 7: stage2<7>(Y, P, lane); break;
-        case 8: stage2<8>(Y, P, lane); break;
-        case 9: stage2<9>(Y, P, lane); break;
-        case 10: stage2<10>(Y, P, lane); break;
-        case 11: stage2<11>(Y, P, lane); break;
-        case 12: stage2<12>(Y, P, lane); break;
-        default: break;
+    for (int i = 0; i < 16; ++i) {
+        // slot 0 writes bins 25 j twice (k1 and 16-k1 are conjugates): same thread, same value class
+        const V2 pw = vfma(xr[i], xr[i], vmul(xi[i], xi[i]));
+        pl[kt.slot_pbin_off[slot][i]] = pw.v;
     }
 }
 
@@ -310,25 +309,48 @@ __device__ __forceinline__ void stage2_dispatch(int slot, const float2* Y, float
 __device__ __forceinline__ int pair_frame_a(int lane) { return lane < 16 ? lane : lane + 16; }
 
 // ---- mel + log10 for one warp's run of filters, 32 frame pairs --------------------------------------
-// Emit(m, log10 pair) consumes the unclamped log-mel values.
+// Emit(m, log10 pair) consumes the unclamped log-mel values of filter m (called in filter order).
 template <class Emit>
-__device__ __forceinline__ float2 mel_stage(const MelParams& mp, const float2* P, int warp, int lane, Emit emit) {
+__device__ __forceinline__ float2 mel_stage(const KernelTables& kt, const float2* P, int warp, int lane, Emit emit) {
     constexpr float kLog10_2 = 0.30102999566398120f;
     float2 mx = make_float2(-INFINITY, -INFINITY);
-    const int m_begin = mp.warp_m0[warp], m_end = mp.warp_m0[warp + 1];
-    for (int m = m_begin; m < m_end; ++m) {
-        const int k0 = mp.k0[m], cnt = mp.cnt[m], e0 = mp.e0[m];
-        const float2* p = P + k0 * 32 + lane;
-        float2 acc = make_float2(0.f, 0.f);
-#pragma unroll 4
-        for (int i = 0; i < cnt; ++i) acc = __ffma2_rn(p[i * 32], mp.w2[e0 + i], acc);
-        // log10(max(acc, 1e-10)) == max(log10(acc), -10): exact -10 for silence (TF-FE:155)
-        float2 lg = __fmul2_rn(make_float2(lg2_approx(acc.x), lg2_approx(acc.y)), make_float2(kLog10_2, kLog10_2));
-        lg.x = fmaxf(lg.x, -10.0f);
-        lg.y = fmaxf(lg.y, -10.0f);
-        emit(m, lg);
-        mx.x = fmaxf(mx.x, lg.x);
-        mx.y = fmaxf(mx.y, lg.y);
+    const int ma = kt.warp_m0[warp], mb = kt.warp_m0[warp + 1];
+    const int kb = kt.warp_kb[warp], ke = kt.warp_ke[warp];
+    int cur = kt.warp_cur[warp];
+    float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+    auto finish = [&](float2 acc) {
+        if (cur >= ma && cur < mb) {
+            // log10(max(acc, 1e-10)) == max(log10(acc), -10): exact -10 for silence (TF-FE:155)
+            float2 lg = __fmul2_rn(make_float2(lg2_approx(acc.x), lg2_approx(acc.y)), make_float2(kLog10_2, kLog10_2));
+            lg.x = fmaxf(lg.x, -10.0f);
+            lg.y = fmaxf(lg.y, -10.0f);
+            emit(cur, lg);
+            mx.x = fmaxf(mx.x, lg.x);
+            mx.y = fmaxf(mx.y, lg.y);
+        }
+        ++cur;
+    };
+    // Two virtual bins past the end (shift 1, no data) flush both accumulators, so `finish` is
+    // instantiated once (code size) and the loop has a single back edge.
+    const float2* p = P + lane;
+    const int k_stop = ma < mb ? ke + 2 : kb;
+#pragma unroll 1
+    for (int k = kb; k < k_stop; ++k) {
+        const bool real = k < ke;
+        int sh = real ? (k == kb ? 0 : kt.shift[k]) : 1;
+#pragma unroll 1
+        while (sh > 0) {
+            finish(acc0);
+            acc0 = acc1;
+            acc1 = make_float2(0.f, 0.f);
+            --sh;
+        }
+        if (real) {
+            const float4 w = kt.w4[k];
+            const float2 pv = p[k * 32];
+            acc0 = __ffma2_rn(pv, make_float2(w.x, w.y), acc0);
+            acc1 = __ffma2_rn(pv, make_float2(w.z, w.w), acc1);
+        }
     }
     return mx;
 }
@@ -351,7 +373,8 @@ logmel_tiles_kernel(const ClipArgs a, const __grid_constant__ MelParams mp, cons
     float2* P = reinterpret_cast<float2*>(smem + kSmemRaw + kSmemY);
     const uint32_t bar = smem_u32(smem + kSmemRaw + kSmemY + kSmemP);
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // tells the compiler it is warp-uniform
     if (tid == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -369,45 +392,47 @@ logmel_tiles_kernel(const ClipArgs a, const __grid_constant__ MelParams mp, cons
     TileCtx cur = tile_ctx(a, item / kTilesPerClip, item % kTilesPerClip);
     if (tid == 0 && cur.active) tile_issue_tma(a, cur, raw, bar);
     uint32_t parity = 0;
-    bool have_prev = false;
+    bool have_cur = true, have_prev = false;
     TileCtx prev = cur;
 
-    auto run_mel = [&](const TileCtx& c) {
-        float* ob = a.out + static_cast<int64_t>(c.b) * a.n_mels * kNFrames;
-        const int fa = c.f0 + pair_frame_a(lane), fb = fa + 16;
-        float2 mx;
-        if (c.active) {
-            mx = mel_stage(mp, P, warp, lane, [&](int m, float2 lg) {
-                float* row = ob + static_cast<int64_t>(m) * kNFrames;
-                if (fa < kNFrames) row[fa] = lg.x;
-                if (fb < kNFrames) row[fb] = lg.y;
-            });
-            if (fa >= kNFrames) mx.x = -INFINITY;
-            if (fb >= kNFrames) mx.y = -INFINITY;
-        } else {
-            // every frame of the tile is digital silence: log10(1e-10) = -10 exactly
-            for (int m = mp.warp_m0[warp]; m < mp.warp_m0[warp + 1]; ++m) {
-                float* row = ob + static_cast<int64_t>(m) * kNFrames;
-                if (fa < kNFrames) row[fa] = -10.0f;
-                if (fb < kNFrames) row[fb] = -10.0f;
-            }
-            mx = make_float2(-10.0f, -10.0f);
-        }
-        float v = fmaxf(mx.x, mx.y);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-        if (lane == 0 && mp.warp_m0[warp] < mp.warp_m0[warp + 1]) atomic_max_float(a.gmax + c.b, v);
-    };
-
+    // One extra trip at the end runs only the mel stage of the last tile, so every stage appears
+    // exactly once in the instruction stream (code size = instruction-cache footprint).
     while (true) {
         // ---- phase X: stage 1 of `cur` (needs raw) + mel of `prev` (needs P) ------------------------
-        if (cur.active) {
+        if (have_cur && cur.active) {
             mbar_wait(bar, parity);
             parity ^= 1;
             if (cur.needs_fix || a.pcm_format == WLM_PCM_I16) tile_fixup(a, cur, raw);
             stage1(raw, Y, wv, tw, warp, lane);
         }
-        if (have_prev) run_mel(prev);
+        if (have_prev) {
+            const TileCtx& c = prev;
+            const int fa = c.f0 + pair_frame_a(lane), fb = fa + 16;
+            float* ob = a.out + static_cast<int64_t>(c.b) * a.n_mels * kNFrames + fa;
+            float2 mx;
+            if (c.active) {
+                mx = mel_stage(mp, P, warp, lane, [&](int m, float2 lg) {
+                    float* row = ob + m * kNFrames;
+                    if (fa < kNFrames) row[0] = lg.x;
+                    if (fb < kNFrames) row[16] = lg.y;
+                });
+                if (fa >= kNFrames) mx.x = -INFINITY;
+                if (fb >= kNFrames) mx.y = -INFINITY;
+            } else {
+                // every frame of the tile is digital silence: log10(1e-10) = -10 exactly
+                for (int m = mp.warp_m0[warp]; m < mp.warp_m0[warp + 1]; ++m) {
+                    float* row = ob + m * kNFrames;
+                    if (fa < kNFrames) row[0] = -10.0f;
+                    if (fb < kNFrames) row[16] = -10.0f;
+                }
+                mx = make_float2(-10.0f, -10.0f);
+            }
+            float v = fmaxf(mx.x, mx.y);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+            if (lane == 0 && mp.warp_m0[warp] < mp.warp_m0[warp + 1]) atomic_max_float(a.gmax + c.b, v);
+        }
+        if (!have_cur) break;
         __syncthreads();
         // raw is free: prefetch the next work item
         const int next_item = item + gridDim.x;
@@ -418,15 +443,14 @@ logmel_tiles_kernel(const ClipArgs a, const __grid_constant__ MelParams mp, cons
             if (tid == 0 && nxt.active) tile_issue_tma(a, nxt, raw, bar);
         }
         // ---- phase Y: stage 2 of `cur` -----------------------------------------------------------
-        if (cur.active && warp < fft::kNumSlots) stage2_dispatch(warp, Y, P, lane);
+        if (cur.active && warp < fft::kNumSlots) stage2(mp, Y, P, warp, lane);
         __syncthreads();
         prev = cur;
         have_prev = true;
-        if (!have_next) break;
+        have_cur = have_next;
         cur = nxt;
         item = next_item;
     }
-    run_mel(prev);
 }
 
 __global__ void init_gmax_kernel(float* gmax, int B) {

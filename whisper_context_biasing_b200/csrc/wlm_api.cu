@@ -202,7 +202,10 @@ extern "C" int wlm_plan_create(int device, int n_mels, const float* mel_dense_ho
 
 #ifdef WLM_HAVE_FUSED
     {
-        fused::build_tables(p->h_sparse, n_mels, &p->h_fused_tables);
+        if (fused::build_tables(p->h_sparse, n_mels, &p->h_fused_tables) != 0) {
+            wlm_plan_destroy(p);
+            return fail(WLM_ERR_UNSUPPORTED, "mel table: a filter has no FFT bin (num_mel_filters too high for 201 bins)");
+        }
         WLM_CUDA_P(cudaMalloc(&p->d_fused_tables, sizeof(fused::Tables)));
         WLM_CUDA_P(cudaMemcpy(p->d_fused_tables, &p->h_fused_tables, sizeof(fused::Tables), cudaMemcpyHostToDevice));
         cudaError_t fe = fused::configure(n_mels, &p->max_clusters);
