@@ -69,24 +69,22 @@ constexpr int kSmemBytes = kSmemRaw + kSmemY + kSmemP + 256;
 constexpr int kCluster = 8;                     // CTAs per clip
 constexpr int kMaxTilesPerCta = (kTilesPerClip + kCluster - 1) / kCluster;   // 6
 constexpr int kMaxFiltersPerWarp = 8;           // 16 warps x 8 >= 128 mels
-constexpr int kMaxBinsPerFilter = 16;
+constexpr int kMaxGroupBins = 16;               // bins between two adjacent filter centres
 constexpr int kTmemColsPerTile = 2 * kMaxFiltersPerWarp;                      // 16 (two frames per filter)
 constexpr int kTmemColsPerWarp = kMaxTilesPerCta * kTmemColsPerTile;          // 96; 4 warps per lane quarter = 384 <= 512
-constexpr int kMaxEntries = 448;
-
-// One (warp, filter) visit of the mel stage.
-struct FilterRef {
-    int16_t poff;   // k0 * 32: float2 offset of the filter's first bin in P
-    int16_t n;      // number of bins (1..16)
-    int16_t e0;     // first weight entry
-    int16_t m;      // filter index (row of the output)
-};
 
 // Everything the kernel reads with warp-uniform indices, passed by value (constant bank).
+//
+// Mel projection: FFT bin k adds w_lo[k] P[k] to filter lo[k] and w_hi[k] P[k] to filter lo[k]+1
+// (host-built from the caller's dense table, weights bit-identical).  Bins with the same lo[k] form
+// a "group" (the bins between two adjacent filter centres).  Warp w owns filters
+// [m0, m0+nf) and walks groups g = 0..nf, group g = bins [gb[g], gb[g+1]) with lo = m0-1+g:
+//     filter m0+q  =  sum_{k in group q} w_hi[k] P[k]  +  sum_{k in group q+1} w_lo[k] P[k]
 struct KernelTables {
-    float2 w2[kMaxEntries];                         // (w, w) per (filter, bin), bit-identical to the caller's table
-    FilterRef fref[kWarps][kMaxFiltersPerWarp];     // filters of warp w
-    int16_t nf[kWarps];                             // how many
+    float4 w4[kNFreq + 3];                          // (w_lo, w_lo, w_hi, w_hi) per bin
+    int16_t gb[kWarps][kMaxFiltersPerWarp + 2];     // group boundaries (bin indices)
+    int16_t m0[kWarps];                             // first filter of warp w
+    int16_t nf[kWarps];                             // number of filters of warp w (<= 8)
     // stage 2: per k2 slot, float2 offsets into Y (component) and into P (output bin) per FFT16 output
     int16_t slot_comp_off[16];                      // comp * 32
     int16_t slot_pbin_off[13][16];                  // output_bin(k1, k2) * 32, indexed by cfft16 array position
@@ -100,7 +98,7 @@ struct Tables {
     KernelTables mel;
 };
 
-// returns 0, or -1 if the table does not fit the fused path (empty filter, support > 16 bins)
+// returns 0, or -1 if the table does not fit the fused path (a group longer than 16 bins)
 inline int build_tables(const MelSparse& sp, int n_mels, Tables* t) {
     for (int n1 = 0; n1 < 16; ++n1)
         for (int tt = 0; tt < 25; ++tt) {
@@ -110,26 +108,21 @@ inline int build_tables(const MelSparse& sp, int n_mels, Tables* t) {
     KernelTables& mp = t->mel;
     memset(&mp, 0, sizeof(mp));
     mp.n_mels = (int16_t)n_mels;
-    int klo[kMaxMels], khi[kMaxMels];
-    for (int m = 0; m < n_mels; ++m) { klo[m] = -1; khi[m] = -1; }
-    for (int k = 0; k < kNFreq; ++k) {
-        if (sp.w_lo[k] != 0.0f && sp.lo[k] >= 0) { const int m = sp.lo[k]; if (klo[m] < 0) klo[m] = k; khi[m] = k; }
-        if (sp.w_hi[k] != 0.0f && sp.lo[k] + 1 < n_mels) { const int m = sp.lo[k] + 1; if (klo[m] < 0) klo[m] = k; khi[m] = k; }
-    }
-    int e0[kMaxMels], e = 0;
-    for (int m = 0; m < n_mels; ++m) {
-        if (klo[m] < 0 || khi[m] - klo[m] + 1 > kMaxBinsPerFilter) return -1;
-        e0[m] = e;
-        for (int k = klo[m]; k <= khi[m]; ++k) {
-            float w = 0.0f;
-            if (sp.lo[k] == m) w = sp.w_lo[k];
-            else if (sp.lo[k] + 1 == m) w = sp.w_hi[k];
-            if (e >= kMaxEntries) return -1;
-            mp.w2[e++] = make_float2(w, w);
+    for (int k = 0; k < kNFreq; ++k) mp.w4[k] = make_float4(sp.w_lo[k], sp.w_lo[k], sp.w_hi[k], sp.w_hi[k]);
+    // first bin of every group: gstart[v] = first k with lo[k] >= v - 1   (v = lo + 1 in 0..n_mels)
+    int gstart[kMaxMels + 2];
+    {
+        int k = 0;
+        for (int v = 0; v <= n_mels + 1; ++v) {
+            while (k < kNFreq && sp.lo[k] + 1 < v) ++k;
+            gstart[v] = k;
         }
     }
-    // contiguous filter runs per warp, balanced on (18 + 3 * bins) issue slots per filter, at most 8 each
-    auto cost = [&](int m) { return 18.0 + 3.0 * (khi[m] - klo[m] + 1); };
+    for (int v = 0; v <= n_mels; ++v)
+        if (gstart[v + 1] - gstart[v] > kMaxGroupBins) return -1;
+    // contiguous filter runs per warp, balanced on issue slots: ~4 per bin of the two groups a filter
+    // touches (shared with its neighbour) + ~12 per filter
+    auto cost = [&](int m) { return 12.0 + 2.0 * (gstart[m + 2] - gstart[m]); };
     double total = 0;
     for (int m = 0; m < n_mels; ++m) total += cost(m);
     int m = 0;
@@ -137,21 +130,20 @@ inline int build_tables(const MelSparse& sp, int n_mels, Tables* t) {
     for (int w = 0; w < kWarps; ++w) {
         const double target = total * (w + 1) / kWarps;
         int cnt = 0;
+        mp.m0[w] = (int16_t)m;
         while (m < n_mels && cnt < kMaxFiltersPerWarp) {
-            const int left_after = n_mels - (m + 1);
             const bool must_take = n_mels - m > (kWarps - 1 - w) * kMaxFiltersPerWarp;   // the rest could not hold them
             if (!must_take && cnt > 0 && acc + 0.5 * cost(m) > target) break;
-            (void)left_after;
-            FilterRef& r = mp.fref[w][cnt];
-            r.poff = (int16_t)(klo[m] * 32);
-            r.n = (int16_t)(khi[m] - klo[m] + 1);
-            r.e0 = (int16_t)e0[m];
-            r.m = (int16_t)m;
             acc += cost(m);
             ++m;
             ++cnt;
         }
         mp.nf[w] = (int16_t)cnt;
+        // groups g = 0..cnt: lo = m0 - 1 + g  ->  v = m0 + g
+        for (int g = 0; g <= kMaxFiltersPerWarp + 1; ++g) {
+            const int v = mp.m0[w] + (g <= cnt + 1 ? g : cnt + 1);
+            mp.gb[w][g] = (int16_t)gstart[v <= n_mels + 1 ? v : n_mels + 1];
+        }
     }
     if (m < n_mels) return -1;
     for (int s2 = 0; s2 < fft::kNumSlots; ++s2) {
@@ -205,6 +197,12 @@ __device__ __forceinline__ void tmem_dealloc_512(uint32_t taddr) {
 }
 __device__ __forceinline__ void tmem_st_x2(uint32_t taddr, float a, float b) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const float2 (&v)[8]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "f"(v[0].x), "f"(v[0].y), "f"(v[1].x), "f"(v[1].y), "f"(v[2].x), "f"(v[2].y), "f"(v[3].x), "f"(v[3].y),
+          "f"(v[4].x), "f"(v[4].y), "f"(v[5].x), "f"(v[5].y), "f"(v[6].x), "f"(v[6].y), "f"(v[7].x), "f"(v[7].y) : "memory");
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, float (&r)[16]) {
@@ -355,45 +353,56 @@ __device__ __forceinline__ void stage2(const KernelTables& kt, const float2* Y, 
 __device__ __forceinline__ int pair_frame_a(int lane) { return lane < 16 ? lane : lane + 16; }
 
 // ---- mel stage ------------------------------------------------------------------------------------
-// One warp, its run of filters, 32 frame pairs.  Per filter: gather-sum over the filter's bins
-// (fall-through switch = one straight-line copy of the 16 possible terms), keep the POWER in tensor
-// memory (two columns: frame a, frame b), track the running max.  log10 is monotone, so the max of
-// the log-mel is the log of this max.
-__device__ __forceinline__ float2 mel_stage(const KernelTables& kt, const float2* P, int warp, int lane,
-                                            uint32_t tcol, float2 mx) {
+// One warp, its run of <= 8 filters, 32 frame pairs.  Groups of bins between adjacent filter centres
+// are walked once: every P value is loaded once and feeds the falling side of one filter and the
+// rising side of the next (two independent FFMA2 chains).  The group loop is unrolled (static
+// register indices for the 8 outputs); inside, a fall-through switch on the group length gives one
+// straight-line copy of the 16 possible terms.  The POWER goes to tensor memory (16 columns:
+// 8 filters x two frames); log10 is monotone, so the running max is kept on the power.
+#define WLM_MEL_TERM(i)                                                            \
+    case (i) + 1: {                                                                \
+        const float4 w = ww[i];                                                    \
+        const float2 pv = pp[(i) * 32];                                            \
+        A = __ffma2_rn(pv, make_float2(w.z, w.w), A);                              \
+        Bq = __ffma2_rn(pv, make_float2(w.x, w.y), Bq);                            \
+    }
+
+__device__ __forceinline__ float2 mel_stage(const KernelTables& kt, const float2* P, int warp, int lane, uint32_t tcol) {
     const int nf = kt.nf[warp];
     const float2* pl = P + lane;
-#pragma unroll 1
-    for (int j = 0; j < nf; ++j) {
-        const FilterRef fr = kt.fref[warp][j];
-        const float2* pp = pl + fr.poff;
-        const float2* ww = kt.w2 + fr.e0;
-        float2 acc = make_float2(0.f, 0.f);
-        switch (fr.n) {
-            case 16: acc = __ffma2_rn(pp[15 * 32], ww[15], acc);
-            case 15: acc = __ffma2_rn(pp[14 * 32], ww[14], acc);
-            case 14: acc = __ffma2_rn(pp[13 * 32], ww[13], acc);
-            case 13: acc = __ffma2_rn(pp[12 * 32], ww[12], acc);
-            case 12: acc = __ffma2_rn(pp[11 * 32], ww[11], acc);
-            case 11: acc = __ffma2_rn(pp[10 * 32], ww[10], acc);
-            case 10: acc = __ffma2_rn(pp[9 * 32], ww[9], acc);
-            case 9: acc = __ffma2_rn(pp[8 * 32], ww[8], acc);
-            case 8: acc = __ffma2_rn(pp[7 * 32], ww[7], acc);
-            case 7: acc = __ffma2_rn(pp[6 * 32], ww[6], acc);
-            case 6: acc = __ffma2_rn(pp[5 * 32], ww[5], acc);
-            case 5: acc = __ffma2_rn(pp[4 * 32], ww[4], acc);
-            case 4: acc = __ffma2_rn(pp[3 * 32], ww[3], acc);
-            case 3: acc = __ffma2_rn(pp[2 * 32], ww[2], acc);
-            case 2: acc = __ffma2_rn(pp[1 * 32], ww[1], acc);
-            case 1: acc = __ffma2_rn(pp[0], ww[0], acc);
-            default: break;
+    float2 out[kMaxFiltersPerWarp];
+#pragma unroll
+    for (int q = 0; q < kMaxFiltersPerWarp; ++q) out[q] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int g = 0; g <= kMaxFiltersPerWarp; ++g) {
+        if (g <= nf) {
+            const int k0 = kt.gb[warp][g];
+            const int n = kt.gb[warp][g + 1] - k0;
+            const float2* pp = pl + k0 * 32;
+            const float4* ww = kt.w4 + k0;
+            float2 A = make_float2(0.f, 0.f), Bq = make_float2(0.f, 0.f);
+            switch (n) {
+                WLM_MEL_TERM(15) WLM_MEL_TERM(14) WLM_MEL_TERM(13) WLM_MEL_TERM(12)
+                WLM_MEL_TERM(11) WLM_MEL_TERM(10) WLM_MEL_TERM(9) WLM_MEL_TERM(8)
+                WLM_MEL_TERM(7) WLM_MEL_TERM(6) WLM_MEL_TERM(5) WLM_MEL_TERM(4)
+                WLM_MEL_TERM(3) WLM_MEL_TERM(2) WLM_MEL_TERM(1) WLM_MEL_TERM(0)
+                default: break;
+            }
+            if (g < kMaxFiltersPerWarp) out[g] = A;                      // rising side of filter m0+g
+            if (g > 0) out[g - 1] = __fadd2_rn(out[g - 1], Bq);          // falling side of filter m0+g-1
         }
-        tmem_st_x2(tcol + 2 * j, acc.x, acc.y);
-        mx.x = fmaxf(mx.x, acc.x);
-        mx.y = fmaxf(mx.y, acc.y);
     }
+    tmem_st_x16(tcol, out);
+    float2 mx = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int q = 0; q < kMaxFiltersPerWarp; ++q)
+        if (q < nf) {
+            mx.x = fmaxf(mx.x, out[q].x);
+            mx.y = fmaxf(mx.y, out[q].y);
+        }
     return mx;
 }
+#undef WLM_MEL_TERM
 
 // log10(max(p, 1e-10)) == max(log10 p, -10): exactly -10 for silence (TF-FE:155); p = 0 -> -inf -> -10
 __device__ __forceinline__ float log10_floor(float p) {
@@ -444,108 +453,146 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
     for (int t = 0; t < 25; ++t) wv[t] = win_lane[n1 * 25 + t];
     const int tw = n1 == 0 ? 25 : (kNfft - 25 * n1 + 15) / 16;
 
+    // The CTA's work is a stream of steps, one per tile it owns (a clip in which it owns no active
+    // tile still contributes one empty step so that it takes part in that clip's cluster barrier).
+    // Step i:   phase X   stage 1 of step i  |  mel of step i-1 (+ CTA max when i-1 ended a clip)
+    //           barrier;  cluster ARRIVE for the clip that just ended;  TMA for step i+1
+    //           phase Y   stage 2 of step i  |  cluster WAIT + output pass of the clip that ended
+    //           barrier
+    // so the clip-end work (max exchange, TMEM read-back, stores) overlaps the next clip's stage 2.
+    struct Step {
+        bool valid, has_tile, last;
+        int j, n_my, tile;
+        ClipCtx cc;
+    };
+    auto first_step_of_clip = [&](int bb) {
+        Step s;
+        s.valid = bb < a.B;
+        s.j = 0;
+        s.tile = rank;
+        s.n_my = 0;
+        s.has_tile = false;
+        s.last = true;
+        if (s.valid) {
+            s.cc = clip_ctx(a, bb);
+            s.n_my = s.cc.n_act > rank ? (s.cc.n_act - rank + kCluster - 1) / kCluster : 0;
+            s.has_tile = s.n_my > 0;
+            s.last = s.n_my <= 1;
+        } else {
+            s.cc.b = bb; s.cc.len = 0; s.cc.n_act = 0; s.cc.base = 0;
+        }
+        return s;
+    };
+    auto next_step = [&](const Step& c) {
+        if (!c.last) {
+            Step s = c;
+            s.j = c.j + 1;
+            s.tile = c.tile + kCluster;
+            s.last = s.j == c.n_my - 1;
+            return s;
+        }
+        return first_step_of_clip(c.cc.b + n_clusters);
+    };
+
     uint32_t parity = 0;
-    int clip_parity = 0;
-    int b = cluster_id;
-    ClipCtx cc;
-    if (b < a.B) {
-        cc = clip_ctx(a, b);
-        if (tid == 0 && rank < cc.n_act) tile_issue_tma(a, cc, rank, raw, bar);
-    }
-    for (; b < a.B; b += n_clusters, clip_parity ^= 1) {
-        const int n_my = cc.n_act > rank ? (cc.n_act - rank + kCluster - 1) / kCluster : 0;
-        const int b_next = b + n_clusters;
-        ClipCtx cn = cc;
-        if (b_next < a.B) cn = clip_ctx(a, b_next);
-        float2 mx = make_float2(0.f, 0.f);   // powers are >= 0
+    int fin_parity = 0;
+    Step cur = first_step_of_clip(cluster_id);
+    Step prev = cur;
+    prev.valid = false;
+    if (tid == 0 && cur.valid && cur.has_tile) tile_issue_tma(a, cur.cc, cur.tile, raw, bar);
+    float2 mx = make_float2(0.f, 0.f);   // running max of the mel power of the clip in flight (>= 0)
 
-        // One extra trip at the end runs only the mel stage of the last tile.
-        for (int j = 0; j <= n_my; ++j) {
-            const int tile = rank + j * kCluster;
-            // ---- phase X: stage 1 of tile j (needs raw) + mel of tile j-1 (needs P) --------------------
-            if (j < n_my) {
-                mbar_wait(bar, parity);
-                parity ^= 1;
-                tile_fixup(a, cc, tile, raw);
-                stage1(raw, Y, wv, tw, warp, lane);
-            }
-            if (j > 0) {
-                float2 m2 = mel_stage(kt, P, warp, lane, twin + (j - 1) * kTmemColsPerTile, make_float2(0.f, 0.f));
-                // frames past 3000 (last tile only) do not exist
-                const int fa = (tile - kCluster) * kTile + pair_frame_a(lane);
-                if (fa < kNFrames) mx.x = fmaxf(mx.x, m2.x);
-                if (fa + 16 < kNFrames) mx.y = fmaxf(mx.y, m2.y);
-            }
-            if (j == n_my) break;
-            __syncthreads();
-            // raw is free: prefetch the next tile of this clip, or the first tile of the next clip
-            if (tid == 0) {
-                if (j + 1 < n_my) tile_issue_tma(a, cc, tile + kCluster, raw, bar);
-                else if (b_next < a.B && rank < cn.n_act) tile_issue_tma(a, cn, rank, raw, bar);
-            }
-            // ---- phase Y: stage 2 of tile j ------------------------------------------------------------
-            if (warp < fft::kNumSlots) stage2(kt, Y, P, warp, lane);
-            __syncthreads();
+    while (cur.valid || prev.valid) {
+        const Step nxt = cur.valid ? next_step(cur) : cur;
+        // ---- phase X -------------------------------------------------------------------------------
+        if (cur.valid && cur.has_tile) {
+            mbar_wait(bar, parity);
+            parity ^= 1;
+            tile_fixup(a, cur.cc, cur.tile, raw);
+            stage1(raw, Y, wv, tw, warp, lane);
         }
-        if (n_my == 0 && tid == 0 && b_next < a.B && rank < cn.n_act) tile_issue_tma(a, cn, rank, raw, bar);
-        tmem_wait_st();
-
-        // ---- per-clip max: warp -> CTA -> cluster (distributed shared memory) -----------------------------
-        float v = fmaxf(mx.x, mx.y);
+        const bool clip_ends = prev.valid && prev.last;
+        if (prev.valid && prev.has_tile) {
+            const float2 m2 = mel_stage(kt, P, warp, lane, twin + prev.j * kTmemColsPerTile);
+            const int fa = prev.tile * kTile + pair_frame_a(lane);     // frames past 3000 do not exist
+            if (fa < kNFrames) mx.x = fmaxf(mx.x, m2.x);
+            if (fa + 16 < kNFrames) mx.y = fmaxf(mx.y, m2.y);
+        }
+        if (clip_ends) {
+            float v = fmaxf(mx.x, mx.y);
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-        if (lane == 0) warp_max[warp] = v;
+            for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+            if (lane == 0) warp_max[warp] = v;
+            mx = make_float2(0.f, 0.f);
+        }
         __syncthreads();
-        if (warp == 0) {
-            float c = lane < kWarps ? warp_max[lane] : 0.f;
+        if (clip_ends) {
+            if (warp == 0) {
+                float c = lane < kWarps ? warp_max[lane] : 0.f;
 #pragma unroll
-            for (int o = 8; o > 0; o >>= 1) c = fmaxf(c, __shfl_xor_sync(0xffffffffu, c, o));
-            if (lane == 0) cta_max[clip_parity] = c;
+                for (int o = 8; o > 0; o >>= 1) c = fmaxf(c, __shfl_xor_sync(0xffffffffu, c, o));
+                if (lane == 0) cta_max[fin_parity] = c;
+            }
+            // split cluster barrier: arrive now (release: cta_max is visible to the peers) ...
+            asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
         }
-        cluster.sync();   // release/acquire: every CTA's cta_max[clip_parity] is visible cluster-wide
-        float pmax = 0.f;
-        if (lane < kCluster) pmax = *cluster.map_shared_rank(cta_max + clip_parity, lane);
+        // raw is free: prefetch the next step's tile
+        if (tid == 0 && nxt.valid && nxt.has_tile && cur.valid) tile_issue_tma(a, nxt.cc, nxt.tile, raw, bar);
+        // ---- phase Y -------------------------------------------------------------------------------
+        if (cur.valid && cur.has_tile && warp < fft::kNumSlots) stage2(kt, Y, P, warp, lane);
+        if (clip_ends) {
+            // ... and wait only here, after this warp's share of stage 2
+            asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+            float pmax = 0.f;
+            if (lane < kCluster) pmax = *cluster.map_shared_rank(cta_max + fin_parity, lane);
 #pragma unroll
-        for (int o = 4; o > 0; o >>= 1) pmax = fmaxf(pmax, __shfl_xor_sync(0xffffffffu, pmax, o));
-        pmax = __shfl_sync(0xffffffffu, pmax, 0);
-        const float gmax = log10_floor(pmax);                 // TF-FE:157
-        const float floor_v = gmax - 8.0f;                    // TF-FE:158
-        if (rank == 0 && tid == 0 && a.gmax) a.gmax[b] = gmax;
+            for (int o = 4; o > 0; o >>= 1) pmax = fmaxf(pmax, __shfl_xor_sync(0xffffffffu, pmax, o));
+            pmax = __shfl_sync(0xffffffffu, pmax, 0);
+            fin_parity ^= 1;
+            const float gmax = log10_floor(pmax);                 // TF-FE:157
+            const float floor_v = fmaxf(gmax - 8.0f, -10.0f);     // TF-FE:158 (log-mel is never below -10)
+            const int bb = prev.cc.b;
+            if (rank == 0 && tid == 0 && a.gmax) a.gmax[bb] = gmax;
 
-        // ---- single output pass: TMEM -> (max(log10, gmax-8)+4)/4 -> HBM -----------------------------------
-        {
-            float* ob = a.out + static_cast<int64_t>(b) * a.n_mels * kNFrames;
+            // single output pass: TMEM -> (max(log10, gmax-8)+4)/4 -> HBM
+            tmem_wait_st();
+            constexpr float kLog10_2 = 0.30102999566398120f;
+            float* ob = a.out + static_cast<int64_t>(bb) * a.n_mels * kNFrames + pair_frame_a(lane);
             const int nf = kt.nf[warp];
-            const int pa = pair_frame_a(lane);
-            for (int j = 0; j < n_my; ++j) {
+            const int m0 = kt.m0[warp];
+            for (int j = 0; j < prev.n_my; ++j) {
                 float r[16];
                 tmem_ld_x16(twin + j * kTmemColsPerTile, r);
-                const int fa = (rank + j * kCluster) * kTile + pa;
-                float* of = ob + fa;
+                const int f0 = (rank + j * kCluster) * kTile;
+                const int fa = f0 + pair_frame_a(lane);
+                float* of = ob + f0 + m0 * kNFrames;
 #pragma unroll
                 for (int q = 0; q < kMaxFiltersPerWarp; ++q) {
                     if (q < nf) {
-                        float* row = of + kt.fref[warp][q].m * kNFrames;
-                        const float oa = (fmaxf(log10_floor(r[2 * q]), floor_v) + 4.0f) * 0.25f;      // TF-FE:161
-                        const float obv = (fmaxf(log10_floor(r[2 * q + 1]), floor_v) + 4.0f) * 0.25f;
-                        if (fa < kNFrames) row[0] = oa;
-                        if (fa + 16 < kNFrames) row[16] = obv;
+                        float2 lg = __fmul2_rn(make_float2(lg2_approx(r[2 * q]), lg2_approx(r[2 * q + 1])),
+                                               make_float2(kLog10_2, kLog10_2));
+                        lg.x = fmaxf(lg.x, floor_v);
+                        lg.y = fmaxf(lg.y, floor_v);
+                        lg = __ffma2_rn(lg, make_float2(0.25f, 0.25f), make_float2(1.0f, 1.0f));   // (x+4)/4, TF-FE:161
+                        if (fa < kNFrames) of[q * kNFrames] = lg.x;
+                        if (fa + 16 < kNFrames) of[q * kNFrames + 16] = lg.y;
                     }
                 }
             }
             // tiles of mine that hold no real sample: log-mel is exactly -10 everywhere
-            const float silent = (fmaxf(-10.0f, floor_v) + 4.0f) * 0.25f;
-            for (int tile = rank + n_my * kCluster; tile < kTilesPerClip; tile += kCluster) {
-                const int fa = tile * kTile + pa;
-                float* of = ob + fa;
+            const float silent = (floor_v + 4.0f) * 0.25f;
+            for (int tile = rank + prev.n_my * kCluster; tile < kTilesPerClip; tile += kCluster) {
+                const int fa = tile * kTile + pair_frame_a(lane);
+                float* of = ob + tile * kTile + m0 * kNFrames;
                 for (int q = 0; q < nf; ++q) {
-                    float* row = of + kt.fref[warp][q].m * kNFrames;
-                    if (fa < kNFrames) row[0] = silent;
-                    if (fa + 16 < kNFrames) row[16] = silent;
+                    if (fa < kNFrames) of[q * kNFrames] = silent;
+                    if (fa + 16 < kNFrames) of[q * kNFrames + 16] = silent;
                 }
             }
         }
-        cc = cn;
+        __syncthreads();
+        prev = cur;
+        cur = nxt;
     }
     // all TMEM reads are complete (tcgen05.wait::ld inside tmem_ld_x16); release the allocation
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

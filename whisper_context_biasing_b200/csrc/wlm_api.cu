@@ -123,12 +123,13 @@ static int build_sparse(const float* dense, int n_mels, MelSparse* sp, std::vect
             sp->lo[k] = (int16_t)idx[0];
             sp->w_lo[k] = dense[k * n_mels + idx[0]];
             sp->w_hi[k] = dense[k * n_mels + idx[1]];
-        } else if (idx[0] == prev_lo + 1) {
-            // single filter, and it is the upper one of the running pair (first interval, a bin
-            // exactly on a filter centre, last interval): keep the pair, weight goes to "hi"
-            sp->lo[k] = (int16_t)prev_lo;
-            sp->w_hi[k] = dense[k * n_mels + idx[0]];
+        } else if (idx[0] == 0 && prev_lo == -1) {
+            // first interval [f0, f1): only the rising side of filter 0 -> "hi" weight of the pair (-1, 0)
+            sp->lo[k] = -1;
+            sp->w_hi[k] = dense[k * n_mels + 0];
         } else {
+            // single filter m elsewhere: filter m-1 is exactly zero here, i.e. the bin sits on the
+            // centre of m or on its falling side with m+1 not started -> "lo" weight of the pair (m, m+1)
             sp->lo[k] = (int16_t)idx[0];
             sp->w_lo[k] = dense[k * n_mels + idx[0]];
         }
