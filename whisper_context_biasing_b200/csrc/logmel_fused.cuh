@@ -45,6 +45,7 @@ using fused::vadd; using fused::vsub; using fused::vmul; using fused::vfma; usin
 }  // namespace wlm
 
 #include "fft_pfa.cuh"
+#include "mel_structure.inc"
 
 namespace wlm {
 namespace fused {
@@ -99,7 +100,9 @@ struct Tables {
 };
 
 // returns 0, or -1 if the table does not fit the fused path (a group longer than 16 bins)
-inline int build_tables(const MelSparse& sp, int n_mels, Tables* t) {
+// *variant receives 80 / 128 when the structure equals the baked Whisper bank (unrolled kernel), else 0
+inline int build_tables(const MelSparse& sp, int n_mels, Tables* t, int* variant) {
+    *variant = 0;
     for (int n1 = 0; n1 < 16; ++n1)
         for (int tt = 0; tt < 25; ++tt) {
             const int n = (25 * n1 + 16 * tt) % 400;
@@ -120,6 +123,12 @@ inline int build_tables(const MelSparse& sp, int n_mels, Tables* t) {
     }
     for (int v = 0; v <= n_mels; ++v)
         if (gstart[v + 1] - gstart[v] > kMaxGroupBins) return -1;
+    const short* baked_g = n_mels == 80 ? kMelGstartHost80 : (n_mels == 128 ? kMelGstartHost128 : nullptr);
+    const short* baked_m0 = n_mels == 80 ? kMelM0Host80 : kMelM0Host128;
+    const short* baked_nf = n_mels == 80 ? kMelNfHost80 : kMelNfHost128;
+    bool same = baked_g != nullptr;
+    for (int v = 0; same && v <= n_mels + 1; ++v) same = gstart[v] == baked_g[v];
+    if (same) *variant = n_mels;
     // contiguous filter runs per warp, balanced on issue slots: ~4 per bin of the two groups a filter
     // touches (shared with its neighbour) + ~12 per filter
     auto cost = [&](int m) { return 12.0 + 2.0 * (gstart[m + 2] - gstart[m]); };
@@ -131,7 +140,12 @@ inline int build_tables(const MelSparse& sp, int n_mels, Tables* t) {
         const double target = total * (w + 1) / kWarps;
         int cnt = 0;
         mp.m0[w] = (int16_t)m;
-        while (m < n_mels && cnt < kMaxFiltersPerWarp) {
+        if (same) {   // partition baked into the unrolled kernel
+            mp.m0[w] = baked_m0[w];
+            cnt = baked_nf[w];
+            m = mp.m0[w] + cnt;
+        }
+        while (!same && m < n_mels && cnt < kMaxFiltersPerWarp) {
             const bool must_take = n_mels - m > (kWarps - 1 - w) * kMaxFiltersPerWarp;   // the rest could not hold them
             if (!must_take && cnt > 0 && acc + 0.5 * cost(m) > target) break;
             acc += cost(m);
@@ -404,6 +418,71 @@ __device__ __forceinline__ float2 mel_stage(const KernelTables& kt, const float2
 }
 #undef WLM_MEL_TERM
 
+// Unrolled variant for the two Whisper banks: group boundaries and the warp's filter run are
+// compile-time constants (mel_structure.inc), so the stage is straight-line code -- one LDS.64 and
+// one 16-byte constant load per bin, FFMA2 straight into statically indexed accumulators.
+template <int NMELS> struct MelFixed;
+template <> struct MelFixed<80> {
+    static __device__ __forceinline__ constexpr int gstart(int v) { return kMelGstart80[v]; }
+    static __device__ __forceinline__ constexpr int m0(int w) { return kMelM0_80[w]; }
+    static __device__ __forceinline__ constexpr int nf(int w) { return kMelNf_80[w]; }
+};
+template <> struct MelFixed<128> {
+    static __device__ __forceinline__ constexpr int gstart(int v) { return kMelGstart128[v]; }
+    static __device__ __forceinline__ constexpr int m0(int w) { return kMelM0_128[w]; }
+    static __device__ __forceinline__ constexpr int nf(int w) { return kMelNf_128[w]; }
+};
+
+template <int NMELS, int W>
+__device__ __forceinline__ float2 mel_fixed_warp(const KernelTables& kt, const float2* P, int lane, uint32_t tcol) {
+    using S = MelFixed<NMELS>;
+    constexpr int nf = S::nf(W), m0 = S::m0(W);
+    const float2* pl = P + lane;
+    float2 out[kMaxFiltersPerWarp];
+#pragma unroll
+    for (int q = 0; q < kMaxFiltersPerWarp; ++q) out[q] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int g = 0; g <= nf; ++g) {
+#pragma unroll
+        for (int k = S::gstart(m0 + g); k < S::gstart(m0 + g + 1); ++k) {
+            const float4 w = kt.w4[k];
+            const float2 pv = pl[k * 32];
+            if (g < nf) out[g] = __ffma2_rn(pv, make_float2(w.z, w.w), out[g]);            // rising side of m0+g
+            if (g > 0) out[g - 1] = __ffma2_rn(pv, make_float2(w.x, w.y), out[g - 1]);     // falling side of m0+g-1
+        }
+    }
+    tmem_st_x16(tcol, out);
+    float2 mx = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int q = 0; q < nf; ++q) {
+        mx.x = fmaxf(mx.x, out[q].x);
+        mx.y = fmaxf(mx.y, out[q].y);
+    }
+    return mx;
+}
+
+template <int NMELS>
+__device__ __forceinline__ float2 mel_fixed(const KernelTables& kt, const float2* P, int warp, int lane, uint32_t tcol) {
+    switch (warp) {
+        case 0: return mel_fixed_warp<NMELS, 0>(kt, P, lane, tcol);
+        case 1: return mel_fixed_warp<NMELS, 1>(kt, P, lane, tcol);
+        case 2: return mel_fixed_warp<NMELS, 2>(kt, P, lane, tcol);
+        case 3: return mel_fixed_warp<NMELS, 3>(kt, P, lane, tcol);
+        case 4: return mel_fixed_warp<NMELS, 4>(kt, P, lane, tcol);
+        case 5: return mel_fixed_warp<NMELS, 5>(kt, P, lane, tcol);
+        case 6: return mel_fixed_warp<NMELS, 6>(kt, P, lane, tcol);
+        case 7: return mel_fixed_warp<NMELS, 7>(kt, P, lane, tcol);
+        case 8: return mel_fixed_warp<NMELS, 8>(kt, P, lane, tcol);
+        case 9: return mel_fixed_warp<NMELS, 9>(kt, P, lane, tcol);
+        case 10: return mel_fixed_warp<NMELS, 10>(kt, P, lane, tcol);
+        case 11: return mel_fixed_warp<NMELS, 11>(kt, P, lane, tcol);
+        case 12: return mel_fixed_warp<NMELS, 12>(kt, P, lane, tcol);
+        case 13: return mel_fixed_warp<NMELS, 13>(kt, P, lane, tcol);
+        case 14: return mel_fixed_warp<NMELS, 14>(kt, P, lane, tcol);
+        default: return mel_fixed_warp<NMELS, 15>(kt, P, lane, tcol);
+    }
+}
+
 // log10(max(p, 1e-10)) == max(log10 p, -10): exactly -10 for silence (TF-FE:155); p = 0 -> -inf -> -10
 __device__ __forceinline__ float log10_floor(float p) {
     constexpr float kLog10_2 = 0.30102999566398120f;
@@ -413,6 +492,8 @@ __device__ __forceinline__ float log10_floor(float p) {
 // ================================================================================================
 // The kernel: persistent clusters of 8 CTAs, one clip per cluster at a time.
 // ================================================================================================
+// NMELS = 80 / 128: unrolled mel stage for the Whisper banks; NMELS = 0: table-driven mel stage.
+template <int NMELS>
 __global__ void __launch_bounds__(kThreads, 1)
 logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt, const float* __restrict__ win_lane) {
     namespace cg = cooperative_groups;
@@ -505,18 +586,27 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
     while (cur.valid || prev.valid) {
         const Step nxt = cur.valid ? next_step(cur) : cur;
         // ---- phase X -------------------------------------------------------------------------------
+        // Stage 1 (FP-pipe bound: packed FFT) and the mel stage of the previous tile (load/issue bound)
+        // are independent; half of the warps of every scheduler run them in the opposite order so the
+        // two kinds of work overlap instead of all warps throttling on the FMA pipe at the same time.
+        const bool clip_ends = prev.valid && prev.last;
+        const bool mel_first = (warp >> 2) & 1;
         if (cur.valid && cur.has_tile) {
             mbar_wait(bar, parity);
             parity ^= 1;
             tile_fixup(a, cur.cc, cur.tile, raw);
-            stage1(raw, Y, wv, tw, warp, lane);
         }
-        const bool clip_ends = prev.valid && prev.last;
-        if (prev.valid && prev.has_tile) {
-            const float2 m2 = mel_stage(kt, P, warp, lane, twin + prev.j * kTmemColsPerTile);
-            const int fa = prev.tile * kTile + pair_frame_a(lane);     // frames past 3000 do not exist
-            if (fa < kNFrames) mx.x = fmaxf(mx.x, m2.x);
-            if (fa + 16 < kNFrames) mx.y = fmaxf(mx.y, m2.y);
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+            if ((pass == 0) != mel_first) {
+                if (cur.valid && cur.has_tile) stage1(raw, Y, wv, tw, warp, lane);
+            } else if (prev.valid && prev.has_tile) {
+                const uint32_t tcol = twin + prev.j * kTmemColsPerTile;
+                const float2 m2 = NMELS == 0 ? mel_stage(kt, P, warp, lane, tcol) : mel_fixed<NMELS == 0 ? 80 : NMELS>(kt, P, warp, lane, tcol);
+                const int fa = prev.tile * kTile + pair_frame_a(lane);     // frames past 3000 do not exist
+                if (fa < kNFrames) mx.x = fmaxf(mx.x, m2.x);
+                if (fa + 16 < kNFrames) mx.y = fmaxf(mx.y, m2.y);
+            }
         }
         if (clip_ends) {
             float v = fmaxf(mx.x, mx.y);
@@ -601,45 +691,51 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
 }
 
 // ---- host side -----------------------------------------------------------------------------------
-inline cudaError_t configure(int /*n_mels*/, int* max_clusters) {
-    cudaError_t e = cudaFuncSetAttribute(logmel_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    if (e != cudaSuccess) return e;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(kCluster * 148);
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = kSmemBytes;
-    cudaLaunchAttribute at[1];
+// variant: 80 / 128 when the table's structure equals the baked one (and the partition was taken from it)
+typedef void (*KernelFn)(const ClipArgs, const KernelTables, const float*);
+inline KernelFn kernel_for(int variant) {
+    if (variant == 80) return logmel_cluster_kernel<80>;
+    if (variant == 128) return logmel_cluster_kernel<128>;
+    return logmel_cluster_kernel<0>;
+}
+
+inline void fill_launch_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* at, int n_clusters, cudaStream_t st) {
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->gridDim = dim3(kCluster * n_clusters);
+    cfg->blockDim = dim3(kThreads);
+    cfg->dynamicSmemBytes = kSmemBytes;
+    cfg->stream = st;
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = kCluster;
     at[0].val.clusterDim.y = 1;
     at[0].val.clusterDim.z = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
+    cfg->attrs = at;
+    cfg->numAttrs = 1;
+}
+
+inline cudaError_t configure(int variant, int* max_clusters) {
+    KernelFn fn = kernel_for(variant);
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute at[1];
+    fill_launch_config(&cfg, at, 148, nullptr);
     int n = 0;
-    e = cudaOccupancyMaxActiveClusters(&n, logmel_cluster_kernel, &cfg);
+    e = cudaOccupancyMaxActiveClusters(&n, fn, &cfg);
     if (e != cudaSuccess) return e;
     if (n < 1) return cudaErrorLaunchOutOfResources;
     *max_clusters = n;
     return cudaSuccess;
 }
 
-inline cudaError_t launch(const ClipArgs& a, const Tables* d_tables, const Tables& h_tables, int /*sm_count*/,
+inline cudaError_t launch(const ClipArgs& a, const Tables* d_tables, const Tables& h_tables, int variant,
                           int max_clusters, cudaStream_t st, int* n_launches) {
     const int n_clusters = a.B < max_clusters ? a.B : max_clusters;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(kCluster * n_clusters);
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = kSmemBytes;
-    cfg.stream = st;
+    cudaLaunchConfig_t cfg;
     cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = kCluster;
-    at[0].val.clusterDim.y = 1;
-    at[0].val.clusterDim.z = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
+    fill_launch_config(&cfg, at, n_clusters, st);
     *n_launches = 1;
-    return cudaLaunchKernelEx(&cfg, logmel_cluster_kernel, a, h_tables.mel, static_cast<const float*>(d_tables->win_lane));
+    return cudaLaunchKernelEx(&cfg, kernel_for(variant), a, h_tables.mel, static_cast<const float*>(d_tables->win_lane));
 }
 
 }  // namespace fused

@@ -70,6 +70,7 @@ struct wlm_plan {
     fused::Tables h_fused_tables;
 #endif
     int max_clusters = 0;          // co-resident clusters of the fused kernel (occupancy query)
+    int variant = 0;               // 80 / 128: unrolled mel stage (Whisper banks); 0: table-driven
 
     // wlm_logmel_host pipeline
     cudaStream_t copy_stream = nullptr;
@@ -203,13 +204,13 @@ extern "C" int wlm_plan_create(int device, int n_mels, const float* mel_dense_ho
 
 #ifdef WLM_HAVE_FUSED
     {
-        if (fused::build_tables(p->h_sparse, n_mels, &p->h_fused_tables) != 0) {
+        if (fused::build_tables(p->h_sparse, n_mels, &p->h_fused_tables, &p->variant) != 0) {
             wlm_plan_destroy(p);
             return fail(WLM_ERR_UNSUPPORTED, "mel table: a filter has no FFT bin (num_mel_filters too high for 201 bins)");
         }
         WLM_CUDA_P(cudaMalloc(&p->d_fused_tables, sizeof(fused::Tables)));
         WLM_CUDA_P(cudaMemcpy(p->d_fused_tables, &p->h_fused_tables, sizeof(fused::Tables), cudaMemcpyHostToDevice));
-        cudaError_t fe = fused::configure(n_mels, &p->max_clusters);
+        cudaError_t fe = fused::configure(p->variant, &p->max_clusters);
         if (fe != cudaSuccess) {
             wlm_plan_destroy(p);
             return fail(WLM_ERR_CUDA, "fused kernel configuration failed: %s", cudaGetErrorString(fe));
@@ -273,7 +274,7 @@ static int launch_logmel(wlm_plan* p, const ClipArgs& a, cudaStream_t st) {
 #ifdef WLM_HAVE_FUSED
     else {
         int n_launches = 0;
-        cudaError_t e = fused::launch(a, p->d_fused_tables, p->h_fused_tables, p->sm_count, p->max_clusters, st, &n_launches);
+        cudaError_t e = fused::launch(a, p->d_fused_tables, p->h_fused_tables, p->variant, p->max_clusters, st, &n_launches);
         if (e != cudaSuccess) return fail(WLM_ERR_CUDA, "fused launch failed: %s", cudaGetErrorString(e));
         p->launches += n_launches;
     }
