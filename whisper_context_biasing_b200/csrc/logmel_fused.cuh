@@ -187,6 +187,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "DONE_%=:\n"
         "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 // TMA 1-D bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -319,7 +322,10 @@ __device__ __forceinline__ void tile_fixup(const ClipArgs& a, const ClipCtx& c, 
 
 // ---- stage 1 ----------------------------------------------------------------------------------
 // warp w, lane (n1 = lane & 15, g = lane >> 4): frames (32 g + w, 32 g + w + 16) of the tile.
-__device__ __forceinline__ void stage1(const float* raw, float2* Y, const float (&wv)[25], int tw, int warp, int lane) {
+// `loaded()` runs once the warp no longer needs the raw buffer, `before_store()` just before Y is written.
+template <class Loaded, class BeforeStore>
+__device__ __forceinline__ void stage1(const float* raw, float2* Y, const float (&wv)[25], int tw, int warp, int lane,
+                                       Loaded loaded, BeforeStore before_store) {
     const int n1 = lane & 15, g = lane >> 4;
     const float* p0 = raw + g * kRegion + kHop * warp + 25 * n1;
     const float* p1 = p0 - kNfft;
@@ -332,6 +338,8 @@ __device__ __forceinline__ void stage1(const float* raw, float2* Y, const float 
     }
     V2 out[25];
     fft::rfft25<V2>(y, out);
+    loaded();
+    before_store();
     float2* yo = Y + n1 * kYStride + (warp + 16 * g);
 #pragma unroll
     for (int c = 0; c < 25; ++c) yo[c * 32] = out[c].v;
@@ -341,7 +349,10 @@ __device__ __forceinline__ void stage1(const float* raw, float2* Y, const float 
 // warp = k2 slot (uniform), lane = frame pair.  One code path for all 13 slots: the slot only selects
 // table offsets, so every warp runs the same instructions (a 13-way templated version thrashed the
 // instruction cache: 28 % of issue stalls were "no instruction").
-__device__ __forceinline__ void stage2(const KernelTables& kt, const float2* Y, float2* P, int slot, int lane) {
+// `loaded()` runs once Y has been read, `before_store()` just before P is written.
+template <class Loaded, class BeforeStore>
+__device__ __forceinline__ void stage2(const KernelTables& kt, const float2* Y, float2* P, int slot, int lane,
+                                       Loaded loaded, BeforeStore before_store) {
     const float2* yl = Y + kt.slot_comp_off[slot] + lane;
     V2 xr[16], xi[16];
 #pragma unroll
@@ -354,12 +365,16 @@ __device__ __forceinline__ void stage2(const KernelTables& kt, const float2* Y, 
         for (int n1 = 0; n1 < 16; ++n1) xi[n1] = mk(0.f, 0.f);
     }
     fft::cfft16<V2>(xr, xi);
+    V2 pw[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) pw[i] = vfma(xr[i], xr[i], vmul(xi[i], xi[i]));
+    loaded();
+    before_store();
     float2* pl = P + lane;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
         // slot 0 writes bins 25 j twice (k1 and 16-k1 are conjugates): same thread, same value class
-        const V2 pw = vfma(xr[i], xr[i], vmul(xi[i], xi[i]));
-        pl[kt.slot_pbin_off[slot][i]] = pw.v;
+        pl[kt.slot_pbin_off[slot][i]] = pw[i].v;
     }
 }
 
@@ -502,10 +517,17 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
     float2* Y = reinterpret_cast<float2*>(smem + kSmemRaw);
     float2* P = reinterpret_cast<float2*>(smem + kSmemRaw + kSmemY);
     unsigned char* misc = smem + kSmemRaw + kSmemY + kSmemP;
-    const uint32_t bar = smem_u32(misc);                               // mbarrier (8 B)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 16);      // TMEM base address
-    float* warp_max = reinterpret_cast<float*>(misc + 32);             // [16]
-    float* cta_max = reinterpret_cast<float*>(misc + 96);              // [2] (clip parity), read by the peers
+    // mbarriers (8 B each).  No CTA-wide barrier separates the stages of a tile: every hand-over between
+    // warps is one of these, so warps drift apart and FMA-bound, load-bound and idle phases overlap.
+    const uint32_t bar_raw = smem_u32(misc);         // TMA landed the tile's PCM            (tx, 1 arrival)
+    const uint32_t bar_yfull = smem_u32(misc + 8);   // all 16 warps stored stage-1 output    (16)
+    const uint32_t bar_yfree = smem_u32(misc + 16);  // all 13 stage-2 warps have read Y      (13)
+    const uint32_t bar_pfull = smem_u32(misc + 24);  // all 13 stage-2 warps stored the power (13)
+    const uint32_t bar_pfree = smem_u32(misc + 32);  // all 16 warps finished the mel stage   (16)
+    uint32_t* raw_readers = reinterpret_cast<uint32_t*>(misc + 40);   // warps done with the raw buffer
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 48);     // TMEM base address
+    float* warp_max = reinterpret_cast<float*>(misc + 64);            // [2][16] (clip parity)
+    float* cta_max = reinterpret_cast<float*>(misc + 192);            // [2] (clip parity), read by the peers
 
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = static_cast<int>(cluster.block_rank());
@@ -515,7 +537,12 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler
     if (tid == 0) {
-        mbar_init(bar, 1);
+        mbar_init(bar_raw, 1);
+        mbar_init(bar_yfull, kWarps);
+        mbar_init(bar_yfree, fft::kNumSlots);
+        mbar_init(bar_pfull, fft::kNumSlots);
+        mbar_init(bar_pfree, kWarps);
+        *raw_readers = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) tmem_alloc_512(smem_u32(tmem_slot));
@@ -536,11 +563,12 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
 
     // The CTA's work is a stream of steps, one per tile it owns (a clip in which it owns no active
     // tile still contributes one empty step so that it takes part in that clip's cluster barrier).
-    // Step i:   phase X   stage 1 of step i  |  mel of step i-1 (+ CTA max when i-1 ended a clip)
-    //           barrier;  cluster ARRIVE for the clip that just ended;  TMA for step i+1
-    //           phase Y   stage 2 of step i  |  cluster WAIT + output pass of the clip that ended
-    //           barrier
-    // so the clip-end work (max exchange, TMEM read-back, stores) overlaps the next clip's stage 2.
+    // Program order of every warp in step i (tile t_i):
+    //   A  stage 1 of t_i            wait raw | ...FFT... | last warp re-arms TMA | wait Y free | store | arrive Y full
+    //   F  output pass of the clip that ended one step ago   (cluster barrier WAIT, TMEM read-back, stores)
+    //   B  mel stage of t_{i-1}      wait P full | ... | arrive P free
+    //   C  stage 2 of t_i (13 warps) wait Y full | load | arrive Y free | FFT | wait P free | store | arrive P full
+    //   D  if t_{i-1} ended a clip:  CTA max -> cta_max, cluster barrier ARRIVE
     struct Step {
         bool valid, has_tile, last;
         int j, n_my, tile;
@@ -574,64 +602,58 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
         }
         return first_step_of_clip(c.cc.b + n_clusters);
     };
+    auto next_tile_step = [&](Step s) {      // first step after `s` that owns a tile (or invalid)
+        do { s = next_step(s); } while (s.valid && !s.has_tile);
+        return s;
+    };
 
-    uint32_t parity = 0;
-    int fin_parity = 0;
+    // Phase bookkeeping: the n-th tile this CTA processes (n = 0, 1, ...) uses phase n of every barrier,
+    // i.e. parity n & 1.  A wait for phase n is only issued by a warp that has already arrived on phase n
+    // or whose own later work is needed to complete phase n+1, so the barrier is never more than one
+    // phase ahead of a waiter.
+    int fin_parity = 0;                      // parity of the clip whose max is exchanged next
     Step cur = first_step_of_clip(cluster_id);
     Step prev = cur;
     prev.valid = false;
-    if (tid == 0 && cur.valid && cur.has_tile) tile_issue_tma(a, cur.cc, cur.tile, raw, bar);
-    float2 mx = make_float2(0.f, 0.f);   // running max of the mel power of the clip in flight (>= 0)
+    int tnum = 0, prev_tnum = 0;             // ordinal of cur's / prev's tile among the tiles of this CTA
+    if (tid == 0) {
+        Step f = cur;
+        if (f.valid && !f.has_tile) f = next_tile_step(f);
+        if (f.valid) tile_issue_tma(a, f.cc, f.tile, raw, bar_raw);
+    }
+    float2 mx = make_float2(0.f, 0.f);       // running max of the mel power of the clip in flight (>= 0)
+    bool pend = false;                       // an output pass is owed (cluster barrier arrived, not yet waited)
+    int pend_b = 0, pend_n_my = 0;
 
-    while (cur.valid || prev.valid) {
-        const Step nxt = cur.valid ? next_step(cur) : cur;
-        // ---- phase X -------------------------------------------------------------------------------
-        // Stage 1 (FP-pipe bound: packed FFT) and the mel stage of the previous tile (load/issue bound)
-        // are independent; half of the warps of every scheduler run them in the opposite order so the
-        // two kinds of work overlap instead of all warps throttling on the FMA pipe at the same time.
-        const bool clip_ends = prev.valid && prev.last;
-        const bool mel_first = (warp >> 2) & 1;
-        if (cur.valid && cur.has_tile) {
-            mbar_wait(bar, parity);
-            parity ^= 1;
+    while (cur.valid || prev.valid || pend) {
+        const bool do_tile = cur.valid && cur.has_tile;
+        // ---- A: stage 1 ----------------------------------------------------------------------------
+        if (do_tile) {
+            mbar_wait(bar_raw, tnum & 1);
             tile_fixup(a, cur.cc, cur.tile, raw);
+            const Step nt = next_tile_step(cur);
+            stage1(raw, Y, wv, tw, warp, lane,
+                   [&]() {   // this warp is done with raw: the last of the 16 re-arms the TMA for the next tile
+                       __syncwarp();
+                       if (lane == 0) {
+                           __threadfence_block();
+                           const uint32_t old = atomicAdd(raw_readers, 1u);
+                           if (old == kWarps - 1) {
+                               *raw_readers = 0;
+                               __threadfence_block();
+                               asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                               if (nt.valid) tile_issue_tma(a, nt.cc, nt.tile, raw, bar_raw);
+                           }
+                       }
+                   },
+                   [&]() {   // stage 2 of the previous tile must have read Y
+                       if (tnum > 0) mbar_wait(bar_yfree, (tnum - 1) & 1);
+                   });
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_yfull);
         }
-#pragma unroll 1
-        for (int pass = 0; pass < 2; ++pass) {
-            if ((pass == 0) != mel_first) {
-                if (cur.valid && cur.has_tile) stage1(raw, Y, wv, tw, warp, lane);
-            } else if (prev.valid && prev.has_tile) {
-                const uint32_t tcol = twin + prev.j * kTmemColsPerTile;
-                const float2 m2 = NMELS == 0 ? mel_stage(kt, P, warp, lane, tcol) : mel_fixed<NMELS == 0 ? 80 : NMELS>(kt, P, warp, lane, tcol);
-                const int fa = prev.tile * kTile + pair_frame_a(lane);     // frames past 3000 do not exist
-                if (fa < kNFrames) mx.x = fmaxf(mx.x, m2.x);
-                if (fa + 16 < kNFrames) mx.y = fmaxf(mx.y, m2.y);
-            }
-        }
-        if (clip_ends) {
-            float v = fmaxf(mx.x, mx.y);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-            if (lane == 0) warp_max[warp] = v;
-            mx = make_float2(0.f, 0.f);
-        }
-        __syncthreads();
-        if (clip_ends) {
-            if (warp == 0) {
-                float c = lane < kWarps ? warp_max[lane] : 0.f;
-#pragma unroll
-                for (int o = 8; o > 0; o >>= 1) c = fmaxf(c, __shfl_xor_sync(0xffffffffu, c, o));
-                if (lane == 0) cta_max[fin_parity] = c;
-            }
-            // split cluster barrier: arrive now (release: cta_max is visible to the peers) ...
-            asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-        }
-        // raw is free: prefetch the next step's tile
-        if (tid == 0 && nxt.valid && nxt.has_tile && cur.valid) tile_issue_tma(a, nxt.cc, nxt.tile, raw, bar);
-        // ---- phase Y -------------------------------------------------------------------------------
-        if (cur.valid && cur.has_tile && warp < fft::kNumSlots) stage2(kt, Y, P, warp, lane);
-        if (clip_ends) {
-            // ... and wait only here, after this warp's share of stage 2
+        // ---- F: output pass of the clip that ended one step ago -----------------------------------------
+        if (pend) {
             asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
             float pmax = 0.f;
             if (lane < kCluster) pmax = *cluster.map_shared_rank(cta_max + fin_parity, lane);
@@ -641,21 +663,19 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
             fin_parity ^= 1;
             const float gmax = log10_floor(pmax);                 // TF-FE:157
             const float floor_v = fmaxf(gmax - 8.0f, -10.0f);     // TF-FE:158 (log-mel is never below -10)
-            const int bb = prev.cc.b;
-            if (rank == 0 && tid == 0 && a.gmax) a.gmax[bb] = gmax;
+            if (rank == 0 && tid == 0 && a.gmax) a.gmax[pend_b] = gmax;
 
-            // single output pass: TMEM -> (max(log10, gmax-8)+4)/4 -> HBM
+            // single pass: TMEM -> (max(log10, gmax-8)+4)/4 -> HBM
             tmem_wait_st();
             constexpr float kLog10_2 = 0.30102999566398120f;
-            float* ob = a.out + static_cast<int64_t>(bb) * a.n_mels * kNFrames + pair_frame_a(lane);
             const int nf = kt.nf[warp];
-            const int m0 = kt.m0[warp];
-            for (int j = 0; j < prev.n_my; ++j) {
+            float* ob = a.out + (static_cast<int64_t>(pend_b) * a.n_mels + kt.m0[warp]) * kNFrames + pair_frame_a(lane);
+            for (int j = 0; j < pend_n_my; ++j) {
                 float r[16];
                 tmem_ld_x16(twin + j * kTmemColsPerTile, r);
                 const int f0 = (rank + j * kCluster) * kTile;
                 const int fa = f0 + pair_frame_a(lane);
-                float* of = ob + f0 + m0 * kNFrames;
+                float* of = ob + f0;
 #pragma unroll
                 for (int q = 0; q < kMaxFiltersPerWarp; ++q) {
                     if (q < nf) {
@@ -671,18 +691,73 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
             }
             // tiles of mine that hold no real sample: log-mel is exactly -10 everywhere
             const float silent = (floor_v + 4.0f) * 0.25f;
-            for (int tile = rank + prev.n_my * kCluster; tile < kTilesPerClip; tile += kCluster) {
+            for (int tile = rank + pend_n_my * kCluster; tile < kTilesPerClip; tile += kCluster) {
                 const int fa = tile * kTile + pair_frame_a(lane);
-                float* of = ob + tile * kTile + m0 * kNFrames;
+                float* of = ob + tile * kTile;
                 for (int q = 0; q < nf; ++q) {
                     if (fa < kNFrames) of[q * kNFrames] = silent;
                     if (fa + 16 < kNFrames) of[q * kNFrames + 16] = silent;
                 }
             }
+            pend = false;
         }
-        __syncthreads();
+        // ---- B: mel stage of the previous tile -------------------------------------------------------------
+        const bool clip_ends = prev.valid && prev.last;
+        const bool mel_tile = prev.valid && prev.has_tile;
+        const int cpar = fin_parity;             // F has run: this is the parity of the clip ending now
+        if (mel_tile) {
+            mbar_wait(bar_pfull, prev_tnum & 1);
+            const uint32_t tcol = twin + prev.j * kTmemColsPerTile;
+            const float2 m2 = NMELS == 0 ? mel_stage(kt, P, warp, lane, tcol) : mel_fixed<NMELS == 0 ? 80 : NMELS>(kt, P, warp, lane, tcol);
+            const int fa = prev.tile * kTile + pair_frame_a(lane);     // frames past 3000 do not exist
+            if (fa < kNFrames) mx.x = fmaxf(mx.x, m2.x);
+            if (fa + 16 < kNFrames) mx.y = fmaxf(mx.y, m2.y);
+            if (clip_ends) {
+                float v = fmaxf(mx.x, mx.y);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+                if (lane == 0) warp_max[cpar * kWarps + warp] = v;
+                mx = make_float2(0.f, 0.f);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_pfree);   // phase prev_tnum
+        }
+        // D: CTA max -> cta_max (every warp writes the same value), cluster ARRIVE.  With data: only after
+        // bar_pfree phase prev_tnum completed (every warp's warp_max is then visible).
+        auto clip_arrive = [&]() {
+            float c = (mel_tile && lane < kWarps) ? warp_max[cpar * kWarps + lane] : 0.f;
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) c = fmaxf(c, __shfl_xor_sync(0xffffffffu, c, o));
+            if (lane == 0) cta_max[cpar] = c;
+            asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+            pend = true;
+            pend_b = prev.cc.b;
+            pend_n_my = prev.n_my;
+        };
+        // ---- C: stage 2 ----------------------------------------------------------------------------------
+        if (do_tile && warp < fft::kNumSlots) {
+            mbar_wait(bar_yfull, tnum & 1);
+            stage2(kt, Y, P, warp, lane,
+                   [&]() {
+                       __syncwarp();
+                       if (lane == 0) mbar_arrive(bar_yfree);   // phase tnum
+                   },
+                   [&]() {   // the mel stage of the previous tile must have read P (all 16 warps)
+                       if (tnum > 0) mbar_wait(bar_pfree, (tnum - 1) & 1);
+                       if (clip_ends) clip_arrive();   // (mel_tile => prev_tnum == tnum - 1: that phase is complete)
+                   });
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_pfull);   // phase tnum
+        }
+        // ---- D for the warps that did not run stage 2 in this step ---------------------------------------------
+        if (clip_ends && !pend) {
+            if (mel_tile) mbar_wait(bar_pfree, prev_tnum & 1);
+            clip_arrive();
+        }
         prev = cur;
-        cur = nxt;
+        prev_tnum = tnum;
+        if (do_tile) ++tnum;
+        cur = cur.valid ? next_step(cur) : cur;
     }
     // all TMEM reads are complete (tcgen05.wait::ld inside tmem_ld_x16); release the allocation
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
