@@ -336,9 +336,9 @@ __device__ __forceinline__ void stage1(const float* raw, float2* Y, const float 
         const float xa = p[16 * t], xb = p[16 * t + 16 * kHop];
         y[t] = mk(xa * wv[t], xb * wv[t]);
     }
+    loaded();      // (fence inside: every LDS above has been performed)
     V2 out[25];
     fft::rfft25<V2>(y, out);
-    loaded();
     before_store();
     float2* yo = Y + n1 * kYStride + (warp + 16 * g);
 #pragma unroll
@@ -564,11 +564,11 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
     // The CTA's work is a stream of steps, one per tile it owns (a clip in which it owns no active
     // tile still contributes one empty step so that it takes part in that clip's cluster barrier).
     // Program order of every warp in step i (tile t_i):
-    //   A  stage 1 of t_i            wait raw | ...FFT... | last warp re-arms TMA | wait Y free | store | arrive Y full
+    //   A  stage 1 of t_i            wait raw | load | last warp re-arms TMA | FFT | wait Y free | store | arrive Y full
     //   F  output pass of the clip that ended one step ago   (cluster barrier WAIT, TMEM read-back, stores)
     //   B  mel stage of t_{i-1}      wait P full | ... | arrive P free
+    //   D  if t_{i-1} ended a clip:  wait P free | CTA max -> cta_max | cluster barrier ARRIVE
     //   C  stage 2 of t_i (13 warps) wait Y full | load | arrive Y free | FFT | wait P free | store | arrive P full
-    //   D  if t_{i-1} ended a clip:  CTA max -> cta_max, cluster barrier ARRIVE
     struct Step {
         bool valid, has_tile, last;
         int j, n_my, tile;
@@ -676,18 +676,23 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
                 const int f0 = (rank + j * kCluster) * kTile;
                 const int fa = f0 + pair_frame_a(lane);
                 float* of = ob + f0;
-#pragma unroll
-                for (int q = 0; q < kMaxFiltersPerWarp; ++q) {
-                    if (q < nf) {
-                        float2 lg = __fmul2_rn(make_float2(lg2_approx(r[2 * q]), lg2_approx(r[2 * q + 1])),
-                                               make_float2(kLog10_2, kLog10_2));
-                        lg.x = fmaxf(lg.x, floor_v);
-                        lg.y = fmaxf(lg.y, floor_v);
-                        lg = __ffma2_rn(lg, make_float2(0.25f, 0.25f), make_float2(1.0f, 1.0f));   // (x+4)/4, TF-FE:161
-                        if (fa < kNFrames) of[q * kNFrames] = lg.x;
-                        if (fa + 16 < kNFrames) of[q * kNFrames + 16] = lg.y;
-                    }
+                const bool va = fa < kNFrames, vb = fa + 16 < kNFrames;
+#define WLM_OUT_ROW(q)                                                                                         \
+    case (q) + 1: {                                                                                            \
+        float2 lg = __fmul2_rn(make_float2(lg2_approx(r[2 * (q)]), lg2_approx(r[2 * (q) + 1])),                \
+                               make_float2(kLog10_2, kLog10_2));                                               \
+        lg.x = fmaxf(lg.x, floor_v);                                                                           \
+        lg.y = fmaxf(lg.y, floor_v);                                                                           \
+        lg = __ffma2_rn(lg, make_float2(0.25f, 0.25f), make_float2(1.0f, 1.0f)); /* (x+4)/4, TF-FE:161 */       \
+        if (va) of[(q) * kNFrames] = lg.x;                                                                     \
+        if (vb) of[(q) * kNFrames + 16] = lg.y;                                                                \
+    }
+                switch (nf) {   // fall-through: exactly nf rows, static register indices
+                    WLM_OUT_ROW(7) WLM_OUT_ROW(6) WLM_OUT_ROW(5) WLM_OUT_ROW(4)
+                    WLM_OUT_ROW(3) WLM_OUT_ROW(2) WLM_OUT_ROW(1) WLM_OUT_ROW(0)
+                    default: break;
                 }
+#undef WLM_OUT_ROW
             }
             // tiles of mine that hold no real sample: log-mel is exactly -10 everywhere
             const float silent = (floor_v + 4.0f) * 0.25f;
@@ -722,9 +727,10 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_pfree);   // phase prev_tnum
         }
-        // D: CTA max -> cta_max (every warp writes the same value), cluster ARRIVE.  With data: only after
-        // bar_pfree phase prev_tnum completed (every warp's warp_max is then visible).
-        auto clip_arrive = [&]() {
+        // ---- D: the clip ended: CTA max -> cta_max (every warp writes the same value), cluster ARRIVE ---------
+        // Done before stage 2 so that the peers get a whole step of slack before anyone WAITs (F, next step).
+        if (clip_ends) {
+            if (mel_tile) mbar_wait(bar_pfree, prev_tnum & 1);   // every warp's warp_max is visible
             float c = (mel_tile && lane < kWarps) ? warp_max[cpar * kWarps + lane] : 0.f;
 #pragma unroll
             for (int o = 8; o > 0; o >>= 1) c = fmaxf(c, __shfl_xor_sync(0xffffffffu, c, o));
@@ -733,7 +739,7 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
             pend = true;
             pend_b = prev.cc.b;
             pend_n_my = prev.n_my;
-        };
+        }
         // ---- C: stage 2 ----------------------------------------------------------------------------------
         if (do_tile && warp < fft::kNumSlots) {
             mbar_wait(bar_yfull, tnum & 1);
@@ -744,15 +750,9 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
                    },
                    [&]() {   // the mel stage of the previous tile must have read P (all 16 warps)
                        if (tnum > 0) mbar_wait(bar_pfree, (tnum - 1) & 1);
-                       if (clip_ends) clip_arrive();   // (mel_tile => prev_tnum == tnum - 1: that phase is complete)
                    });
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_pfull);   // phase tnum
-        }
-        // ---- D for the warps that did not run stage 2 in this step ---------------------------------------------
-        if (clip_ends && !pend) {
-            if (mel_tile) mbar_wait(bar_pfree, prev_tnum & 1);
-            clip_arrive();
         }
         prev = cur;
         prev_tnum = tnum;
