@@ -77,7 +77,7 @@ void run_fp(const char* name, int sms, double ops_per_iter_per_thread, int threa
     cudaFree(out); cudaFree(cyc);
 }
 
-__global__ void __cluster_dims__(1, 1, 1) dummy_cluster_kernel(float* p) { extern __shared__ float s[]; if (p) p[0] = s[0]; }
+__global__ void dummy_cluster_kernel(float* p) { extern __shared__ float s[]; if (p) p[0] = s[0]; }
 
 int main() {
     int dev = 0; CK(cudaSetDevice(dev));
@@ -85,7 +85,8 @@ int main() {
     const int sms = prop.multiProcessorCount;
     printf("device %s  SMs %d  clock %d kHz  smem/SM %zu  smem/block optin %zu\n", prop.name, sms, prop.clockRate,
            prop.sharedMemPerMultiprocessor, prop.sharedMemPerBlockOptin);
-    for (int threads : {128, 256, 512}) {
+    for (int threads : {512}) {
+      if (getenv("UBENCH_FP")) {
         run_fp<0>("scalar FFMA (2 per slot pair)", sms, 2.0 * ILP, threads);
         run_fp<1>("FFMA2", sms, 2.0 * ILP, threads);
         run_fp<2>("FADD2", sms, 2.0 * ILP, threads);
@@ -96,11 +97,12 @@ int main() {
         run_fp<6>("FFMA2 + LDS.64 per 4", sms, 2.0 * ILP, threads);
         run_fp<7>("scalar FFMA + LDS.32 per 4 pairs", sms, 2.0 * ILP, threads);
         run_fp<8>("FFMA2 + (LDS.64+STS.64) per 4", sms, 2.0 * ILP, threads);
+      }
     }
     // co-resident clusters
-    for (int cs : {1, 2, 4, 8, 16}) {
-        for (int smem_kb : {48, 100, 160, 200, 220}) {
-            for (int threads : {256, 512}) {
+    for (int cs : {1, 2, 3, 4, 5, 6, 7, 8, 16}) {
+        for (int smem_kb : {100, 197}) {
+            for (int threads : {512}) {
                 cudaLaunchConfig_t cfg = {};
                 cfg.gridDim = dim3(cs * 64); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem_kb * 1024;
                 cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;

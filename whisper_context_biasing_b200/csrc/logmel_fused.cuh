@@ -1,7 +1,7 @@
 // Fused log-mel kernel for sm_100a.
 //
-// A thread-block CLUSTER of 8 CTAs owns one clip (3000 frames = 47 tiles of 64 frames, tile t goes to
-// CTA t mod 8).  Each CTA (16 warps) walks its tiles through
+// A thread-block CLUSTER of 6 CTAs owns one clip (3000 frames = 47 tiles of 64 frames, tile t goes to
+// CTA t mod 6).  Each CTA (16 warps) walks its tiles through
 //
 //   TMA (cp.async.bulk, mbarrier)  raw PCM  ->  shared memory, two regions 16 banks apart
 //   stage 1  per warp: 4 frames x 16 sub-transforms; lane = (n1, frame group); 25-point real DFT of
@@ -12,7 +12,7 @@
 //
 // with the prime-factor index maps of fft_pfa.cuh (no twiddles between the stages).  All arithmetic on
 // the data path is FADD2 / FMUL2 / FFMA2 on (frame a, frame b) pairs with immediate constants.
-// When the clip is done the 8 CTAs exchange their maxima through distributed shared memory
+// When the clip is done the 6 CTAs exchange their maxima through distributed shared memory
 // (one cluster barrier), and a single pass reads the retained mel power back (tcgen05.ld) and writes
 // (max(log10(max(p,1e-10)), gmax - 8) + 4) / 4 -- the features touch HBM exactly once.
 //
@@ -67,12 +67,14 @@ constexpr int kSmemY = kYFloat2 * 8;            // 102,528
 constexpr int kSmemP = kPFloat2 * 8;            // 51,456
 constexpr int kSmemBytes = kSmemRaw + kSmemY + kSmemP + 256;
 
-constexpr int kCluster = 8;                     // CTAs per clip
-constexpr int kMaxTilesPerCta = (kTilesPerClip + kCluster - 1) / kCluster;   // 6
+constexpr int kCluster = 6;                     // CTAs per clip: 22 co-resident clusters = 132 of 148 SMs (size 8: 15 = 120)
+constexpr int kMaxTilesPerCta = (kTilesPerClip + kCluster - 1) / kCluster;   // 8
 constexpr int kMaxFiltersPerWarp = 8;           // 16 warps x 8 >= 128 mels
 constexpr int kMaxGroupBins = 16;               // bins between two adjacent filter centres
 constexpr int kTmemColsPerTile = 2 * kMaxFiltersPerWarp;                      // 16 (two frames per filter)
-constexpr int kTmemColsPerWarp = kMaxTilesPerCta * kTmemColsPerTile;          // 96; 4 warps per lane quarter = 384 <= 512
+constexpr int kTmemColsPerWarp = kMaxTilesPerCta * kTmemColsPerTile;          // 128; 4 warps per lane quarter = 512 columns
+static_assert(4 * kTmemColsPerWarp <= 512, "the retained mel power must fit the 512 TMEM columns");
+static_assert(kCluster <= 8, "max reduction over the cluster uses 8 lanes");
 
 // Everything the kernel reads with warp-uniform indices, passed by value (constant bank).
 //
