@@ -285,7 +285,7 @@ def run_ours(args, wl, rank, world, local_rank):
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel for one launch of the
 # default workload, from the `ncu --set full` capture summarised under profiles/ (None = not
 # captured yet for this kernel version).
-KERNEL_DRAM_TRAFFIC_BYTES = {80: None, 128: None}
+KERNEL_DRAM_TRAFFIC_BYTES = {80: 700240384, 128: None}   # profiles/r01_step7_cluster6_summary.txt: 491.59 + 208.66 MB
 
 
 def cpu_baseline(n_mels):
