@@ -52,6 +52,7 @@ namespace fused {
 
 constexpr int kTile = 64;                 // frames per tile
 constexpr int kWarps = 16;
+constexpr int kTeamWarps = 8;                 // warps 0..7: TMA + stage 1; warps 8..15: stage 2, mel, output
 constexpr int kThreads = kWarps * 32;
 constexpr int kTilesPerClip = (kNFrames + kTile - 1) / kTile;  // 47
 constexpr int kRegion = 31 * kHop + kNfft;                     // 5360 samples: frames 0..31 of a half tile
@@ -283,29 +284,33 @@ __device__ __forceinline__ void tile_issue_tma(const ClipArgs& a, const ClipCtx&
 
 // int16 -> float32 expansion in place (staging sits in the byte range of region B) + reflect /
 // zero-fill patching of every position outside [0, len).  Only edge tiles and int16 input pay.
-__device__ __forceinline__ void tile_fixup(const ClipArgs& a, const ClipCtx& c, int tile, float* raw) {
-    const int tid = threadIdx.x;
+// Executed by the 256 threads of the stage-1 team (named barrier 1).
+constexpr int kTeamThreads = 256;
+__device__ __forceinline__ void team_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__device__ __forceinline__ void tile_fixup(const ClipArgs& a, const ClipCtx& c, int tile, float* raw, int tid) {
     const int s0 = tile_s0(tile);
     if (a.pcm_format == WLM_PCM_I16) {
         const int16_t* st = reinterpret_cast<const int16_t*>(raw + kRegion);
         constexpr float kScale = 1.0f / 32768.0f;
-        for (int i = tid; i < kRegion; i += kThreads) raw[i] = static_cast<float>(st[i]) * kScale;
-        float tmp[(kRegion + kThreads - 1) / kThreads];
+        constexpr int kPer = (kRegion + kTeamThreads - 1) / kTeamThreads;
+        for (int i = tid; i < kRegion; i += kTeamThreads) raw[i] = static_cast<float>(st[i]) * kScale;
+        float tmp[kPer];
 #pragma unroll
-        for (int j = 0; j < (kRegion + kThreads - 1) / kThreads; ++j) {
-            const int i = tid + j * kThreads;
+        for (int j = 0; j < kPer; ++j) {
+            const int i = tid + j * kTeamThreads;
             tmp[j] = i < kRegion ? static_cast<float>(st[kRegion + i]) * kScale : 0.f;
         }
-        __syncthreads();
+        team_sync();
 #pragma unroll
-        for (int j = 0; j < (kRegion + kThreads - 1) / kThreads; ++j) {
-            const int i = tid + j * kThreads;
+        for (int j = 0; j < kPer; ++j) {
+            const int i = tid + j * kTeamThreads;
             if (i < kRegion) raw[kRegion + i] = tmp[j];
         }
-        __syncthreads();
+        team_sync();
     }
     if (s0 < 0 || s0 + kTileSamples > c.len) {
-        for (int idx = tid; idx < kRawFloats; idx += kThreads) {
+        for (int idx = tid; idx < kRawFloats; idx += kTeamThreads) {
             const int r = idx >= kRegion ? 1 : 0;
             const int s = s0 + r * kRegionStep + (idx - r * kRegion);
             if (s >= 0 && s < c.len) continue;
@@ -318,7 +323,7 @@ __device__ __forceinline__ void tile_fixup(const ClipArgs& a, const ClipCtx& c, 
             }
             raw[idx] = v;
         }
-        __syncthreads();
+        team_sync();
     }
 }
 
@@ -519,17 +524,17 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
     float2* Y = reinterpret_cast<float2*>(smem + kSmemRaw);
     float2* P = reinterpret_cast<float2*>(smem + kSmemRaw + kSmemY);
     unsigned char* misc = smem + kSmemRaw + kSmemY + kSmemP;
-    // mbarriers (8 B each).  No CTA-wide barrier separates the stages of a tile: every hand-over between
-    // warps is one of these, so warps drift apart and FMA-bound, load-bound and idle phases overlap.
-    const uint32_t bar_raw = smem_u32(misc);         // TMA landed the tile's PCM            (tx, 1 arrival)
-    const uint32_t bar_yfull = smem_u32(misc + 8);   // all 16 warps stored stage-1 output    (16)
-    const uint32_t bar_yfree = smem_u32(misc + 16);  // all 13 stage-2 warps have read Y      (13)
-    const uint32_t bar_pfull = smem_u32(misc + 24);  // all 13 stage-2 warps stored the power (13)
-    const uint32_t bar_pfree = smem_u32(misc + 32);  // all 16 warps finished the mel stage   (16)
-    uint32_t* raw_readers = reinterpret_cast<uint32_t*>(misc + 40);   // warps done with the raw buffer
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 48);     // TMEM base address
-    float* warp_max = reinterpret_cast<float*>(misc + 64);            // [2][16] (clip parity)
-    float* cta_max = reinterpret_cast<float*>(misc + 192);            // [2] (clip parity), read by the peers
+    // mbarriers (8 B each).  No CTA-wide barrier in steady state: every hand-over is one of these.
+    const uint32_t bar_raw = smem_u32(misc);         // TMA landed the tile's PCM                  (tx, 1 arrival)
+    const uint32_t bar_yfull = smem_u32(misc + 8);   // the 8 stage-1 warps stored their output     (8)
+    const uint32_t bar_yfree = smem_u32(misc + 16);  // the 8 stage-2 warps have read Y             (8)
+    const uint32_t bar_pfull = smem_u32(misc + 24);  // the 8 stage-2 warps stored the power        (8)
+    const uint32_t bar_pfree = smem_u32(misc + 32);  // the 8 stage-2 warps finished the mel stage  (8)
+    const uint32_t bar_clip0 = smem_u32(misc + 40);  // [2]: every CTA of the cluster delivered its max (kCluster)
+    uint32_t* raw_readers = reinterpret_cast<uint32_t*>(misc + 56);   // stage-1 warps done with the raw buffer
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 60);     // TMEM base address
+    float* warp_max = reinterpret_cast<float*>(misc + 64);            // [2][8] (clip parity)
+    float* clip_max = reinterpret_cast<float*>(misc + 128);           // [2][8]: written by the PEERS (DSMEM)
 
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = static_cast<int>(cluster.block_rank());
@@ -540,37 +545,24 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler
     if (tid == 0) {
         mbar_init(bar_raw, 1);
-        mbar_init(bar_yfull, kWarps);
-        mbar_init(bar_yfree, fft::kNumSlots);
-        mbar_init(bar_pfull, fft::kNumSlots);
-        mbar_init(bar_pfree, kWarps);
+        mbar_init(bar_yfull, kTeamWarps);
+        mbar_init(bar_yfree, kTeamWarps);
+        mbar_init(bar_pfull, kTeamWarps);
+        mbar_init(bar_pfree, kTeamWarps);
+        mbar_init(bar_clip0, kCluster);
+        mbar_init(bar_clip0 + 8, kCluster);
         *raw_readers = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) tmem_alloc_512(smem_u32(tmem_slot));
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    cluster.sync();          // every CTA's barriers exist before a peer may arrive on them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
-    // this warp's TMEM window: lane quarter (warp & 3), 96 columns at (warp >> 2) * 96
-    const uint32_t twin = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) +
-                          static_cast<uint32_t>((warp >> 2) * kTmemColsPerWarp);
-
-    // per-lane stage-1 constants
-    const int n1 = lane & 15;
-    float wv[25];
-#pragma unroll
-    for (int t = 0; t < 25; ++t) wv[t] = win_lane[n1 * 25 + t];
-    const int tw = n1 == 0 ? 25 : (kNfft - 25 * n1 + 15) / 16;
 
     // The CTA's work is a stream of steps, one per tile it owns (a clip in which it owns no active
-    // tile still contributes one empty step so that it takes part in that clip's cluster barrier).
-    // Program order of every warp in step i (tile t_i):
-    //   A  stage 1 of t_i            wait raw | load | last warp re-arms TMA | FFT | wait Y free | store | arrive Y full
-    //   F  output pass of the clip that ended one step ago   (cluster barrier WAIT, TMEM read-back, stores)
-    //   B  mel stage of t_{i-1}      wait P full | ... | arrive P free
-    //   D  if t_{i-1} ended a clip:  wait P free | CTA max -> cta_max | cluster barrier ARRIVE
-    //   C  stage 2 of t_i (13 warps) wait Y full | load | arrive Y free | FFT | wait P free | store | arrive P full
+    // tile still contributes one empty step so that it delivers a max for that clip).  The n-th tile
+    // of the CTA uses phase n (parity n & 1) of every barrier.
     struct Step {
         bool valid, has_tile, last;
         int j, n_my, tile;
@@ -609,76 +601,98 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
         return s;
     };
 
-    // Phase bookkeeping: the n-th tile this CTA processes (n = 0, 1, ...) uses phase n of every barrier,
-    // i.e. parity n & 1.  A wait for phase n is only issued by a warp that has already arrived on phase n
-    // or whose own later work is needed to complete phase n+1, so the barrier is never more than one
-    // phase ahead of a waiter.
-    int fin_parity = 0;                      // parity of the clip whose max is exchanged next
-    Step cur = first_step_of_clip(cluster_id);
-    Step prev = cur;
-    prev.valid = false;
-    int tnum = 0, prev_tnum = 0;             // ordinal of cur's / prev's tile among the tiles of this CTA
-    if (tid == 0) {
-        Step f = cur;
-        if (f.valid && !f.has_tile) f = next_tile_step(f);
-        if (f.valid) tile_issue_tma(a, f.cc, f.tile, raw, bar_raw);
-    }
-    float2 mx = make_float2(0.f, 0.f);       // running max of the mel power of the clip in flight (>= 0)
-    bool pend = false;                       // an output pass is owed (cluster barrier arrived, not yet waited)
-    int pend_b = 0, pend_n_my = 0;
+    if (warp < kTeamWarps) {
+        // ========================= team A: TMA + stage 1 (producer of Y) ===================================
+        const int n1 = lane & 15;
+        float wv[25];
+#pragma unroll
+        for (int t = 0; t < 25; ++t) wv[t] = win_lane[n1 * 25 + t];
+        const int tw = n1 == 0 ? 25 : (kNfft - 25 * n1 + 15) / 16;
 
-    while (cur.valid || prev.valid || pend) {
-        const bool do_tile = cur.valid && cur.has_tile;
-        // ---- A: stage 1 ----------------------------------------------------------------------------
-        if (do_tile) {
+        Step cur = first_step_of_clip(cluster_id);
+        if (cur.valid && !cur.has_tile) cur = next_tile_step(cur);
+        if (tid == 0 && cur.valid) tile_issue_tma(a, cur.cc, cur.tile, raw, bar_raw);
+        for (int tnum = 0; cur.valid; ++tnum) {
             mbar_wait(bar_raw, tnum & 1);
-            tile_fixup(a, cur.cc, cur.tile, raw);
+            tile_fixup(a, cur.cc, cur.tile, raw, tid);
             const Step nt = next_tile_step(cur);
-            stage1(raw, Y, wv, tw, warp, lane,
-                   [&]() {   // this warp is done with raw: the last of the 16 re-arms the TMA for the next tile
-                       __syncwarp();
-                       if (lane == 0) {
-                           __threadfence_block();
-                           const uint32_t old = atomicAdd(raw_readers, 1u);
-                           if (old == kWarps - 1) {
-                               *raw_readers = 0;
-                               __threadfence_block();
-                               asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                               if (nt.valid) tile_issue_tma(a, nt.cc, nt.tile, raw, bar_raw);
+#pragma unroll 1
+            for (int pass = 0; pass < 2; ++pass) {
+                stage1(raw, Y, wv, tw, warp + pass * kTeamWarps, lane,
+                       [&]() {   // second pass loaded: this warp is done with raw; the last of the 8 re-arms the TMA
+                           if (pass == 1) {
+                               __syncwarp();
+                               if (lane == 0) {
+                                   __threadfence_block();
+                                   const uint32_t old = atomicAdd(raw_readers, 1u);
+                                   if (old == kTeamWarps - 1) {
+                                       *raw_readers = 0;
+                                       __threadfence_block();
+                                       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                                       if (nt.valid) tile_issue_tma(a, nt.cc, nt.tile, raw, bar_raw);
+                                   }
+                               }
                            }
-                       }
-                   },
-                   [&]() {   // stage 2 of the previous tile must have read Y
-                       if (tnum > 0) mbar_wait(bar_yfree, (tnum - 1) & 1);
-                   });
+                       },
+                       [&]() {   // stage 2 of the previous tile must have read Y
+                           if (pass == 0 && tnum > 0) mbar_wait(bar_yfree, (tnum - 1) & 1);
+                       });
+            }
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_yfull);
+            cur = nt;
         }
-        // ---- F: output pass of the clip that ended one step ago -----------------------------------------
-        if (pend) {
-            asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-            float pmax = 0.f;
-            if (lane < kCluster) pmax = *cluster.map_shared_rank(cta_max + fin_parity, lane);
-#pragma unroll
-            for (int o = 4; o > 0; o >>= 1) pmax = fmaxf(pmax, __shfl_xor_sync(0xffffffffu, pmax, o));
-            pmax = __shfl_sync(0xffffffffu, pmax, 0);
-            fin_parity ^= 1;
-            const float gmax = log10_floor(pmax);                 // TF-FE:157
-            const float floor_v = fmaxf(gmax - 8.0f, -10.0f);     // TF-FE:158 (log-mel is never below -10)
-            if (rank == 0 && tid == 0 && a.gmax) a.gmax[pend_b] = gmax;
+    } else {
+        // ========================= team B: stage 2, mel, clip max, output (consumer of Y) ======================
+        const int bw = warp - kTeamWarps;                       // 0..7, scheduler bw & 3
+        // Stage-2 slots of this warp: bw and bw + 8 (13 slots: warps 0..4 run two, 5..7 one); the warps
+        // with one slot take three of the 16 mel runs, the others one or two, so the team is balanced.
+        const int n_slots = bw + kTeamWarps < fft::kNumSlots ? 2 : 1;
+        const int n_runs = bw >= 5 ? 3 : ((bw & 3) == 0 ? 2 : 1);
+        auto run_of = [&](int i) { return bw >= 5 ? bw + 4 * i : (i == 0 ? bw : bw + 8); };   // 5:{5,9,13} 0:{0,8} 4:{4,12}
+        // TMEM windows (128 columns each, 4 per lane quarter): quarter q = bw & 3 hosts warp q (first) and q + 4
+        const int win0 = bw < 4 ? 0 : ((bw & 3) == 0 ? 2 : 1);
+        const uint32_t tquart = tmem_base + (static_cast<uint32_t>((bw & 3) * 32) << 16);
 
-            // single pass: TMEM -> (max(log10, gmax-8)+4)/4 -> HBM
-            tmem_wait_st();
-            constexpr float kLog10_2 = 0.30102999566398120f;
-            const int nf = kt.nf[warp];
-            float* ob = a.out + (static_cast<int64_t>(pend_b) * a.n_mels + kt.m0[warp]) * kNFrames + pair_frame_a(lane);
-            for (int j = 0; j < pend_n_my; ++j) {
-                float r[16];
-                tmem_ld_x16(twin + j * kTmemColsPerTile, r);
-                const int f0 = (rank + j * kCluster) * kTile;
-                const int fa = f0 + pair_frame_a(lane);
-                float* of = ob + f0;
-                const bool va = fa < kNFrames, vb = fa + 16 < kNFrames;
+        Step cur = first_step_of_clip(cluster_id);
+        Step prev = cur;
+        prev.valid = false;
+        int tnum = 0, prev_tnum = 0;         // ordinal of cur's / prev's tile among the tiles of this CTA
+        int clip_ord = 0;                    // ordinal of the clip whose max is exchanged next
+        float2 mx = make_float2(0.f, 0.f);   // running max of the mel power of the clip in flight (>= 0)
+        bool pend = false;                   // an output pass is owed (max delivered, peers not yet awaited)
+        int pend_b = 0, pend_n_my = 0, pend_ord = 0;
+
+        while (cur.valid || prev.valid || pend) {
+            const bool do_tile = cur.valid && cur.has_tile;
+            // ---- F: output pass of the clip that ended one step ago ---------------------------------------
+            if (pend) {
+                const int par = pend_ord & 1;
+                mbar_wait(bar_clip0 + 8 * par, (pend_ord >> 1) & 1);
+                float pmax = lane < kCluster ? clip_max[par * 8 + lane] : 0.f;
+#pragma unroll
+                for (int o = 4; o > 0; o >>= 1) pmax = fmaxf(pmax, __shfl_xor_sync(0xffffffffu, pmax, o));
+                pmax = __shfl_sync(0xffffffffu, pmax, 0);
+                const float gmax = log10_floor(pmax);                 // TF-FE:157
+                const float floor_v = fmaxf(gmax - 8.0f, -10.0f);     // TF-FE:158 (log-mel is never below -10)
+                if (rank == 0 && bw == 0 && lane == 0 && a.gmax) a.gmax[pend_b] = gmax;
+
+                // single pass: TMEM -> (max(log10, gmax-8)+4)/4 -> HBM
+                tmem_wait_st();
+                constexpr float kLog10_2 = 0.30102999566398120f;
+                const float silent = (floor_v + 4.0f) * 0.25f;
+                for (int i = 0; i < n_runs; ++i) {
+                    const int run = run_of(i);
+                    const int nf = kt.nf[run];
+                    const uint32_t twin = tquart + static_cast<uint32_t>((win0 + i) * kTmemColsPerWarp);
+                    float* ob = a.out + (static_cast<int64_t>(pend_b) * a.n_mels + kt.m0[run]) * kNFrames + pair_frame_a(lane);
+                    for (int j = 0; j < pend_n_my; ++j) {
+                        float r[16];
+                        tmem_ld_x16(twin + j * kTmemColsPerTile, r);
+                        const int f0 = (rank + j * kCluster) * kTile;
+                        const int fa = f0 + pair_frame_a(lane);
+                        float* of = ob + f0;
+                        const bool va = fa < kNFrames, vb = fa + 16 < kNFrames;
 #define WLM_OUT_ROW(q)                                                                                         \
     case (q) + 1: {                                                                                            \
         float2 lg = __fmul2_rn(make_float2(lg2_approx(r[2 * (q)]), lg2_approx(r[2 * (q) + 1])),                \
@@ -689,81 +703,103 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
         if (va) of[(q) * kNFrames] = lg.x;                                                                     \
         if (vb) of[(q) * kNFrames + 16] = lg.y;                                                                \
     }
-                switch (nf) {   // fall-through: exactly nf rows, static register indices
-                    WLM_OUT_ROW(7) WLM_OUT_ROW(6) WLM_OUT_ROW(5) WLM_OUT_ROW(4)
-                    WLM_OUT_ROW(3) WLM_OUT_ROW(2) WLM_OUT_ROW(1) WLM_OUT_ROW(0)
-                    default: break;
-                }
+                        switch (nf) {   // fall-through: exactly nf rows, static register indices
+                            WLM_OUT_ROW(7) WLM_OUT_ROW(6) WLM_OUT_ROW(5) WLM_OUT_ROW(4)
+                            WLM_OUT_ROW(3) WLM_OUT_ROW(2) WLM_OUT_ROW(1) WLM_OUT_ROW(0)
+                            default: break;
+                        }
 #undef WLM_OUT_ROW
-            }
-            // tiles of mine that hold no real sample: log-mel is exactly -10 everywhere
-            const float silent = (floor_v + 4.0f) * 0.25f;
-            for (int tile = rank + pend_n_my * kCluster; tile < kTilesPerClip; tile += kCluster) {
-                const int fa = tile * kTile + pair_frame_a(lane);
-                float* of = ob + tile * kTile;
-                for (int q = 0; q < nf; ++q) {
-                    if (fa < kNFrames) of[q * kNFrames] = silent;
-                    if (fa + 16 < kNFrames) of[q * kNFrames + 16] = silent;
+                    }
+                    // tiles of mine that hold no real sample: log-mel is exactly -10 everywhere
+                    for (int tile = rank + pend_n_my * kCluster; tile < kTilesPerClip; tile += kCluster) {
+                        const int fa = tile * kTile + pair_frame_a(lane);
+                        float* of = ob + tile * kTile;
+                        for (int q = 0; q < nf; ++q) {
+                            if (fa < kNFrames) of[q * kNFrames] = silent;
+                            if (fa + 16 < kNFrames) of[q * kNFrames + 16] = silent;
+                        }
+                    }
                 }
+                pend = false;
             }
-            pend = false;
-        }
-        // ---- B: mel stage of the previous tile -------------------------------------------------------------
-        const bool clip_ends = prev.valid && prev.last;
-        const bool mel_tile = prev.valid && prev.has_tile;
-        const int cpar = fin_parity;             // F has run: this is the parity of the clip ending now
-        if (mel_tile) {
-            mbar_wait(bar_pfull, prev_tnum & 1);
-            const uint32_t tcol = twin + prev.j * kTmemColsPerTile;
-            const float2 m2 = NMELS == 0 ? mel_stage(kt, P, warp, lane, tcol) : mel_fixed<NMELS == 0 ? 80 : NMELS>(kt, P, warp, lane, tcol);
-            const int fa = prev.tile * kTile + pair_frame_a(lane);     // frames past 3000 do not exist
-            if (fa < kNFrames) mx.x = fmaxf(mx.x, m2.x);
-            if (fa + 16 < kNFrames) mx.y = fmaxf(mx.y, m2.y);
+            // ---- B: mel stage of the previous tile ---------------------------------------------------------
+            const bool clip_ends = prev.valid && prev.last;
+            const bool mel_tile = prev.valid && prev.has_tile;
+            const int cpar = clip_ord & 1;
+            if (mel_tile) {
+                mbar_wait(bar_pfull, prev_tnum & 1);
+                float2 m2 = make_float2(0.f, 0.f);
+                for (int i = 0; i < n_runs; ++i) {
+                    const uint32_t tcol = tquart + static_cast<uint32_t>((win0 + i) * kTmemColsPerWarp + prev.j * kTmemColsPerTile);
+                    const float2 r2 = NMELS == 0 ? mel_stage(kt, P, run_of(i), lane, tcol)
+                                                 : mel_fixed<NMELS == 0 ? 80 : NMELS>(kt, P, run_of(i), lane, tcol);
+                    m2.x = fmaxf(m2.x, r2.x);
+                    m2.y = fmaxf(m2.y, r2.y);
+                }
+                const int fa = prev.tile * kTile + pair_frame_a(lane);     // frames past 3000 do not exist
+                if (fa < kNFrames) mx.x = fmaxf(mx.x, m2.x);
+                if (fa + 16 < kNFrames) mx.y = fmaxf(mx.y, m2.y);
+                if (clip_ends) {
+                    float v = fmaxf(mx.x, mx.y);
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+                    if (lane == 0) warp_max[cpar * 8 + bw] = v;
+                    mx = make_float2(0.f, 0.f);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_pfree);   // phase prev_tnum
+            }
+            // ---- D: the clip ended: deliver the CTA's max to every CTA of the cluster (DSMEM) ---------------------
             if (clip_ends) {
-                float v = fmaxf(mx.x, mx.y);
+                if (bw == 0) {
+                    if (mel_tile) mbar_wait(bar_pfree, prev_tnum & 1);   // every warp's warp_max is visible
+                    float c = (mel_tile && lane < kTeamWarps) ? warp_max[cpar * 8 + lane] : 0.f;
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-                if (lane == 0) warp_max[cpar * kWarps + warp] = v;
-                mx = make_float2(0.f, 0.f);
+                    for (int o = 4; o > 0; o >>= 1) c = fmaxf(c, __shfl_xor_sync(0xffffffffu, c, o));
+                    c = __shfl_sync(0xffffffffu, c, 0);
+                    if (lane < kCluster) {
+                        // remote store into peer `lane`'s clip_max[cpar][rank], then arrive on its clip barrier
+                        uint32_t rslot, rbar;
+                        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rslot) : "r"(smem_u32(clip_max + cpar * 8 + rank)), "r"(lane));
+                        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(bar_clip0 + 8 * cpar), "r"(lane));
+                        asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(rslot), "f"(c) : "memory");
+                        asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(rbar) : "memory");
+                    }
+                }
+                pend = true;
+                pend_b = prev.cc.b;
+                pend_n_my = prev.n_my;
+                pend_ord = clip_ord;
+                ++clip_ord;
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_pfree);   // phase prev_tnum
+            // ---- C: stage 2 --------------------------------------------------------------------------------
+            if (do_tile) {
+                mbar_wait(bar_yfull, tnum & 1);
+#pragma unroll 1
+                for (int i = 0; i < n_slots; ++i) {
+                    stage2(kt, Y, P, bw + i * kTeamWarps, lane,
+                           [&]() {
+                               if (i == n_slots - 1) {
+                                   __syncwarp();
+                                   if (lane == 0) mbar_arrive(bar_yfree);   // phase tnum
+                               }
+                           },
+                           [&]() {   // the mel stage of the previous tile must have read P (all 8 warps)
+                               if (i == 0 && tnum > 0) mbar_wait(bar_pfree, (tnum - 1) & 1);
+                           });
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_pfull);   // phase tnum
+            }
+            prev = cur;
+            prev_tnum = tnum;
+            if (do_tile) ++tnum;
+            cur = cur.valid ? next_step(cur) : cur;
         }
-        // ---- D: the clip ended: CTA max -> cta_max (every warp writes the same value), cluster ARRIVE ---------
-        // Done before stage 2 so that the peers get a whole step of slack before anyone WAITs (F, next step).
-        if (clip_ends) {
-            if (mel_tile) mbar_wait(bar_pfree, prev_tnum & 1);   // every warp's warp_max is visible
-            float c = (mel_tile && lane < kWarps) ? warp_max[cpar * kWarps + lane] : 0.f;
-#pragma unroll
-            for (int o = 8; o > 0; o >>= 1) c = fmaxf(c, __shfl_xor_sync(0xffffffffu, c, o));
-            if (lane == 0) cta_max[cpar] = c;
-            asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-            pend = true;
-            pend_b = prev.cc.b;
-            pend_n_my = prev.n_my;
-        }
-        // ---- C: stage 2 ----------------------------------------------------------------------------------
-        if (do_tile && warp < fft::kNumSlots) {
-            mbar_wait(bar_yfull, tnum & 1);
-            stage2(kt, Y, P, warp, lane,
-                   [&]() {
-                       __syncwarp();
-                       if (lane == 0) mbar_arrive(bar_yfree);   // phase tnum
-                   },
-                   [&]() {   // the mel stage of the previous tile must have read P (all 16 warps)
-                       if (tnum > 0) mbar_wait(bar_pfree, (tnum - 1) & 1);
-                   });
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_pfull);   // phase tnum
-        }
-        prev = cur;
-        prev_tnum = tnum;
-        if (do_tile) ++tnum;
-        cur = cur.valid ? next_step(cur) : cur;
     }
     // all TMEM reads are complete (tcgen05.wait::ld inside tmem_ld_x16); release the allocation
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    cluster.sync();   // also keeps every CTA's shared memory alive until its peers have read cta_max
+    cluster.sync();   // no CTA leaves while a peer may still write its clip_max / arrive on its barriers
     if (warp == 0) tmem_dealloc_512(tmem_base);
 }
 
