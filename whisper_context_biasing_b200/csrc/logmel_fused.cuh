@@ -50,21 +50,25 @@ using fused::vadd; using fused::vsub; using fused::vmul; using fused::vfma; usin
 namespace wlm {
 namespace fused {
 
-constexpr int kTile = 64;                 // frames per tile
+constexpr int kTile = 64;                 // frames per tile (unit of the mel stage, TMEM slot, output pass)
+constexpr int kHalf = 32;                 // frames per half tile (unit of TMA, stage 1 and stage 2)
 constexpr int kWarps = 16;
-constexpr int kTeamWarps = 8;                 // warps 0..7: TMA + stage 1; warps 8..15: stage 2, mel, output
+constexpr int kTeamWarps = 8;             // warps 0..7: TMA + stage 1; warps 8..15: stage 2, mel, output
+constexpr int kStage2Warps = 7;           // 13 k2 slots, two per warp (lanes 0-15 / 16-31)
 constexpr int kThreads = kWarps * 32;
 constexpr int kTilesPerClip = (kNFrames + kTile - 1) / kTile;  // 47
-constexpr int kRegion = 31 * kHop + kNfft;                     // 5360 samples: frames 0..31 of a half tile
-constexpr int kRegionStep = 32 * kHop;                         // 5120: region B starts 32 frames later
-constexpr int kRawFloats = 2 * kRegion;                        // 10720 (5360 = 16 mod 32: regions 16 banks apart)
-constexpr int kTileSamples = 63 * kHop + kNfft;                // 10480
-constexpr int kYStride = 801;                                  // float2 per n1 row (25*32 + 1: odd)
-constexpr int kYFloat2 = 16 * kYStride;
+// raw PCM of a half tile: two regions of 16 frames each, 2800 samples = 16 (mod 32): 16 banks apart
+constexpr int kRegion = 15 * kHop + kNfft;                     // 2800 samples: frames 0..15 of a half tile
+constexpr int kRegionStep = 16 * kHop;                         // 2560: region B starts 16 frames later
+constexpr int kRawFloats = 2 * kRegion;                        // 5600 per buffer
+constexpr int kHalfSamples = 31 * kHop + kNfft;                // 5360
+constexpr int kYStride = 401;                                  // float2 per n1 row (25 comps x 16 pairs + 1: odd)
+constexpr int kYFloat2 = 16 * kYStride;                        // per buffer
 constexpr int kPFloat2 = kNFreq * 32;
+static_assert(kRegion % 32 == 16, "the two raw regions must sit 16 banks apart");
 
-constexpr int kSmemRaw = kRawFloats * 4;        // 42,880
-constexpr int kSmemY = kYFloat2 * 8;            // 102,528
+constexpr int kSmemRaw = 2 * kRawFloats * 4;    // 44,800  (double buffered)
+constexpr int kSmemY = 2 * kYFloat2 * 8;        // 102,656 (double buffered)
 constexpr int kSmemP = kPFloat2 * 8;            // 51,456
 constexpr int kSmemBytes = kSmemRaw + kSmemY + kSmemP + 256;
 
@@ -251,11 +255,12 @@ __device__ __forceinline__ ClipCtx clip_ctx(const ClipArgs& a, int b) {
     c.n_act = min(kTilesPerClip, (c.len + kNfft / 2 + kTile * kHop - 1) / (kTile * kHop));
     return c;
 }
-__device__ __forceinline__ int tile_s0(int tile) { return tile * (kTile * kHop) - kNfft / 2; }
+// first sample (clip coordinates, may be negative) of half `hh` of tile `tile`
+__device__ __forceinline__ int half_s0(int tile, int hh) { return (tile * kTile + hh * kHalf) * kHop - kNfft / 2; }
 
-// issued by one thread: both regions of the tile, valid sample range only
-__device__ __forceinline__ void tile_issue_tma(const ClipArgs& a, const ClipCtx& c, int tile, float* raw, uint32_t bar) {
-    const int s0 = tile_s0(tile);
+// issued by one thread: both regions of the half tile, valid sample range only
+__device__ __forceinline__ void half_issue_tma(const ClipArgs& a, const ClipCtx& c, int tile, int hh, float* raw, uint32_t bar) {
+    const int s0 = half_s0(tile, hh);
     const int esz = a.pcm_format == WLM_PCM_I16 ? 2 : 4;
     const int gran = 16 / esz;
     const int len_up = min((c.len + gran - 1) / gran * gran, kNSamples);
@@ -269,7 +274,7 @@ __device__ __forceinline__ void tile_issue_tma(const ClipArgs& a, const ClipCtx&
         n[r] = max(hi - lo[r], 0);
         total += static_cast<uint32_t>(n[r]) * esz;
     }
-    mbar_expect_tx(bar, total);
+    mbar_expect_tx(bar, total);      // (total may be 0 for a half that lies past the clip: completes at once)
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
         if (n[r] <= 0) continue;
@@ -283,13 +288,13 @@ __device__ __forceinline__ void tile_issue_tma(const ClipArgs& a, const ClipCtx&
 }
 
 // int16 -> float32 expansion in place (staging sits in the byte range of region B) + reflect /
-// zero-fill patching of every position outside [0, len).  Only edge tiles and int16 input pay.
+// zero-fill patching of every position outside [0, len).  Only edge halves and int16 input pay.
 // Executed by the 256 threads of the stage-1 team (named barrier 1).
 constexpr int kTeamThreads = 256;
 __device__ __forceinline__ void team_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-__device__ __forceinline__ void tile_fixup(const ClipArgs& a, const ClipCtx& c, int tile, float* raw, int tid) {
-    const int s0 = tile_s0(tile);
+__device__ __forceinline__ void half_fixup(const ClipArgs& a, const ClipCtx& c, int tile, int hh, float* raw, int tid) {
+    const int s0 = half_s0(tile, hh);
     if (a.pcm_format == WLM_PCM_I16) {
         const int16_t* st = reinterpret_cast<const int16_t*>(raw + kRegion);
         constexpr float kScale = 1.0f / 32768.0f;
@@ -309,7 +314,7 @@ __device__ __forceinline__ void tile_fixup(const ClipArgs& a, const ClipCtx& c, 
         }
         team_sync();
     }
-    if (s0 < 0 || s0 + kTileSamples > c.len) {
+    if (s0 < 0 || s0 + kHalfSamples > c.len) {
         for (int idx = tid; idx < kRawFloats; idx += kTeamThreads) {
             const int r = idx >= kRegion ? 1 : 0;
             const int s = s0 + r * kRegionStep + (idx - r * kRegion);
@@ -319,7 +324,7 @@ __device__ __forceinline__ void tile_fixup(const ClipArgs& a, const ClipCtx& c, 
             float v = 0.f;
             if (sr >= 0 && sr < c.len) {
                 const int u = sr - s0;
-                if (u >= 0 && u < kTileSamples) v = raw[u < kRegion ? u : kRegion + (u - kRegionStep)];
+                if (u >= 0 && u < kHalfSamples) v = raw[u < kRegion ? u : kRegion + (u - kRegionStep)];
             }
             raw[idx] = v;
         }
@@ -328,65 +333,89 @@ __device__ __forceinline__ void tile_fixup(const ClipArgs& a, const ClipCtx& c, 
 }
 
 // ---- stage 1 ----------------------------------------------------------------------------------
-// warp w, lane (n1 = lane & 15, g = lane >> 4): frames (32 g + w, 32 g + w + 16) of the tile.
+// Half tile of 32 frames = 16 pairs of adjacent frames (2p, 2p+1).  Team warp a (0..7), lane
+// (n1 = lane & 15, g = lane >> 4): pair p = a + 8 g, i.e. frames 2a, 2a+1 of region g.
 // `loaded()` runs once the warp no longer needs the raw buffer, `before_store()` just before Y is written.
 template <class Loaded, class BeforeStore>
-__device__ __forceinline__ void stage1(const float* raw, float2* Y, const float (&wv)[25], int tw, int warp, int lane,
+__device__ __forceinline__ void stage1(const float* raw, float2* Y, const float (&wv)[25], int tw, int a, int lane,
                                        Loaded loaded, BeforeStore before_store) {
     const int n1 = lane & 15, g = lane >> 4;
-    const float* p0 = raw + g * kRegion + kHop * warp + 25 * n1;
+    const float* p0 = raw + g * kRegion + 2 * kHop * a + 25 * n1;
     const float* p1 = p0 - kNfft;
     V2 y[25];
 #pragma unroll
     for (int t = 0; t < 25; ++t) {
         const float* p = (t >= tw) ? p1 : p0;
-        const float xa = p[16 * t], xb = p[16 * t + 16 * kHop];
+        const float xa = p[16 * t], xb = p[16 * t + kHop];
         y[t] = mk(xa * wv[t], xb * wv[t]);
     }
     loaded();      // (fence inside: every LDS above has been performed)
     V2 out[25];
     fft::rfft25<V2>(y, out);
     before_store();
-    float2* yo = Y + n1 * kYStride + (warp + 16 * g);
+    float2* yo = Y + n1 * kYStride + (a + 8 * g);
 #pragma unroll
-    for (int c = 0; c < 25; ++c) yo[c * 32] = out[c].v;
+    for (int c = 0; c < 25; ++c) yo[c * 16] = out[c].v;
 }
 
 // ---- stage 2 ----------------------------------------------------------------------------------
-// warp = k2 slot (uniform), lane = frame pair.  One code path for all 13 slots: the slot only selects
-// table offsets, so every warp runs the same instructions (a 13-way templated version thrashed the
-// instruction cache: 28 % of issue stalls were "no instruction").
+// One warp = two k2 slots x 16 frame pairs: lane = (pair = lane & 15, which slot = lane >> 4).  The slot
+// only selects per-lane offsets (component inside Y, output bins inside P), so all 7 warps run the
+// same instructions (a 13-way templated version thrashed the instruction cache).
+struct Stage2Lane {
+    int comp_off;        // float2 offset of the slot's real component inside a Y row (comp * 16)
+    bool real, active;   // k2 = 0 slot (no imaginary part) / lane has a slot at all
+    uint32_t pbin[8];    // 16 x 16-bit: P row offset (bin * 32) of cfft16 output i, two per register
+};
+__device__ __forceinline__ Stage2Lane stage2_lane_setup(const KernelTables& kt, int bw, int lane) {
+    Stage2Lane L;
+    const int slot = 2 * bw + (lane >> 4);
+    L.active = slot < fft::kNumSlots;
+    const int sl = L.active ? slot : fft::kNumSlots - 1;
+    L.real = sl == 0;
+    L.comp_off = kt.slot_comp_off[sl] / 2;      // table holds comp * 32
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        L.pbin[i] = static_cast<uint32_t>(static_cast<uint16_t>(kt.slot_pbin_off[sl][2 * i])) |
+                    (static_cast<uint32_t>(static_cast<uint16_t>(kt.slot_pbin_off[sl][2 * i + 1])) << 16);
+    return L;
+}
+
 // `loaded()` runs once Y has been read, `before_store()` just before P is written.
 template <class Loaded, class BeforeStore>
-__device__ __forceinline__ void stage2(const KernelTables& kt, const float2* Y, float2* P, int slot, int lane,
+__device__ __forceinline__ void stage2(const Stage2Lane& L, bool warp_has_real, const float2* Y, float2* P, int hh, int lane,
                                        Loaded loaded, BeforeStore before_store) {
-    const float2* yl = Y + kt.slot_comp_off[slot] + lane;
+    const float2* yl = Y + L.comp_off + (lane & 15);
     V2 xr[16], xi[16];
 #pragma unroll
-    for (int n1 = 0; n1 < 16; ++n1) xr[n1].v = yl[n1 * kYStride];
-    if (slot != 0) {
+    for (int n1 = 0; n1 < 16; ++n1) {
+        xr[n1].v = yl[n1 * kYStride];
+        xi[n1].v = yl[n1 * kYStride + 16];
+    }
+    loaded();      // (mbarrier.arrive is a release: the loads above are ordered before it)
+    if (warp_has_real) {   // k2 = 0: Y is purely real; the "imaginary" load fetched the next component
 #pragma unroll
-        for (int n1 = 0; n1 < 16; ++n1) xi[n1].v = yl[n1 * kYStride + 32];
-    } else {  // k2 = 0: Y is purely real
-#pragma unroll
-        for (int n1 = 0; n1 < 16; ++n1) xi[n1] = mk(0.f, 0.f);
+        for (int n1 = 0; n1 < 16; ++n1)
+            if (L.real) xi[n1] = mk(0.f, 0.f);
     }
     fft::cfft16<V2>(xr, xi);
     V2 pw[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) pw[i] = vfma(xr[i], xr[i], vmul(xi[i], xi[i]));
-    loaded();
     before_store();
-    float2* pl = P + lane;
+    if (L.active) {
+        float2* pl = P + 16 * hh + (lane & 15);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        // slot 0 writes bins 25 j twice (k1 and 16-k1 are conjugates): same thread, same value class
-        pl[kt.slot_pbin_off[slot][i]] = pw[i].v;
+        for (int i = 0; i < 16; ++i) {
+            // slot 0 writes bins 25 j twice (k1 and 16-k1 are conjugates): same thread, same value class
+            const uint32_t off = (i & 1) ? (L.pbin[i >> 1] >> 16) : (L.pbin[i >> 1] & 0xffffu);
+            pl[off] = pw[i].v;
+        }
     }
 }
 
-// lane = frame pair: frames (lane, lane+16) for lane < 16, (lane+16, lane+32) for lane >= 16
-__device__ __forceinline__ int pair_frame_a(int lane) { return lane < 16 ? lane : lane + 16; }
+// lane = frame pair of the tile: frames (2 lane, 2 lane + 1)
+__device__ __forceinline__ int pair_frame_a(int lane) { return 2 * lane; }
 
 // ---- mel stage ------------------------------------------------------------------------------------
 // One warp, its run of <= 8 filters, 32 frame pairs.  Groups of bins between adjacent filter centres
@@ -520,21 +549,21 @@ __global__ void __launch_bounds__(kThreads, 1)
 logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt, const float* __restrict__ win_lane) {
     namespace cg = cooperative_groups;
     extern __shared__ __align__(128) unsigned char smem[];
-    float* raw = reinterpret_cast<float*>(smem);
-    float2* Y = reinterpret_cast<float2*>(smem + kSmemRaw);
-    float2* P = reinterpret_cast<float2*>(smem + kSmemRaw + kSmemY);
+    float* raw = reinterpret_cast<float*>(smem);                                   // [2][kRawFloats]
+    float2* Y = reinterpret_cast<float2*>(smem + kSmemRaw);                       // [2][kYFloat2]
+    float2* P = reinterpret_cast<float2*>(smem + kSmemRaw + kSmemY);              // [201][32]
     unsigned char* misc = smem + kSmemRaw + kSmemY + kSmemP;
     // mbarriers (8 B each).  No CTA-wide barrier in steady state: every hand-over is one of these.
-    const uint32_t bar_raw = smem_u32(misc);         // TMA landed the tile's PCM                  (tx, 1 arrival)
-    const uint32_t bar_yfull = smem_u32(misc + 8);   // the 8 stage-1 warps stored their output     (8)
-    const uint32_t bar_yfree = smem_u32(misc + 16);  // the 8 stage-2 warps have read Y             (8)
-    const uint32_t bar_pfull = smem_u32(misc + 24);  // the 8 stage-2 warps stored the power        (8)
-    const uint32_t bar_pfree = smem_u32(misc + 32);  // the 8 stage-2 warps finished the mel stage  (8)
-    const uint32_t bar_clip0 = smem_u32(misc + 40);  // [2]: every CTA of the cluster delivered its max (kCluster)
-    uint32_t* raw_readers = reinterpret_cast<uint32_t*>(misc + 56);   // stage-1 warps done with the raw buffer
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 60);     // TMEM base address
-    float* warp_max = reinterpret_cast<float*>(misc + 64);            // [2][8] (clip parity)
-    float* clip_max = reinterpret_cast<float*>(misc + 128);           // [2][8]: written by the PEERS (DSMEM)
+    const uint32_t bar_raw0 = smem_u32(misc);         // [2] TMA landed the half tile's PCM              (tx, 1 arrival)
+    const uint32_t bar_yfull0 = smem_u32(misc + 16);  // [2] the 8 stage-1 warps stored their output       (8)
+    const uint32_t bar_yfree0 = smem_u32(misc + 32);  // [2] the 7 stage-2 warps have read Y               (7)
+    const uint32_t bar_pfull = smem_u32(misc + 48);   //     the 7 stage-2 warps stored both halves' power (7)
+    const uint32_t bar_pfree = smem_u32(misc + 56);   //     the 8 team-B warps finished the mel stage     (8)
+    const uint32_t bar_clip0 = smem_u32(misc + 64);   // [2] every CTA of the cluster delivered its max    (kCluster)
+    uint32_t* raw_readers = reinterpret_cast<uint32_t*>(misc + 80);   // [2] stage-1 warps done with raw buffer i
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 88);     // TMEM base address
+    float* warp_max = reinterpret_cast<float*>(misc + 96);            // [2][8] (clip parity)
+    float* clip_max = reinterpret_cast<float*>(misc + 160);           // [2][8]: written by the PEERS (DSMEM)
 
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = static_cast<int>(cluster.block_rank());
@@ -544,14 +573,15 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler
     if (tid == 0) {
-        mbar_init(bar_raw, 1);
-        mbar_init(bar_yfull, kTeamWarps);
-        mbar_init(bar_yfree, kTeamWarps);
-        mbar_init(bar_pfull, kTeamWarps);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(bar_raw0 + 8 * i, 1);
+            mbar_init(bar_yfull0 + 8 * i, kTeamWarps);
+            mbar_init(bar_yfree0 + 8 * i, kStage2Warps);
+            mbar_init(bar_clip0 + 8 * i, kCluster);
+            raw_readers[i] = 0;
+        }
+        mbar_init(bar_pfull, kStage2Warps);
         mbar_init(bar_pfree, kTeamWarps);
-        mbar_init(bar_clip0, kCluster);
-        mbar_init(bar_clip0 + 8, kCluster);
-        *raw_readers = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) tmem_alloc_512(smem_u32(tmem_slot));
@@ -561,8 +591,9 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
     const uint32_t tmem_base = *tmem_slot;
 
     // The CTA's work is a stream of steps, one per tile it owns (a clip in which it owns no active
-    // tile still contributes one empty step so that it delivers a max for that clip).  The n-th tile
-    // of the CTA uses phase n (parity n & 1) of every barrier.
+    // tile still contributes one empty step so that it delivers a max for that clip).  A tile is two
+    // half tiles; half h of the CTA's n-th tile uses buffer h (raw and Y) and phase n (parity n & 1)
+    // of the per-buffer barriers; the per-tile barriers (P full / P free) use phase n as well.
     struct Step {
         bool valid, has_tile, last;
         int j, n_my, tile;
@@ -611,47 +642,50 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
 
         Step cur = first_step_of_clip(cluster_id);
         if (cur.valid && !cur.has_tile) cur = next_tile_step(cur);
-        if (tid == 0 && cur.valid) tile_issue_tma(a, cur.cc, cur.tile, raw, bar_raw);
+        if (tid == 0 && cur.valid) {
+            half_issue_tma(a, cur.cc, cur.tile, 0, raw, bar_raw0);
+            half_issue_tma(a, cur.cc, cur.tile, 1, raw + kRawFloats, bar_raw0 + 8);
+        }
         for (int tnum = 0; cur.valid; ++tnum) {
-            mbar_wait(bar_raw, tnum & 1);
-            tile_fixup(a, cur.cc, cur.tile, raw, tid);
             const Step nt = next_tile_step(cur);
 #pragma unroll 1
-            for (int pass = 0; pass < 2; ++pass) {
-                stage1(raw, Y, wv, tw, warp + pass * kTeamWarps, lane,
-                       [&]() {   // second pass loaded: this warp is done with raw; the last of the 8 re-arms the TMA
-                           if (pass == 1) {
-                               __syncwarp();
-                               if (lane == 0) {
+            for (int hh = 0; hh < 2; ++hh) {
+                float* rawb = raw + hh * kRawFloats;
+                mbar_wait(bar_raw0 + 8 * hh, tnum & 1);
+                half_fixup(a, cur.cc, cur.tile, hh, rawb, tid);
+                stage1(rawb, Y + hh * kYFloat2, wv, tw, warp, lane,
+                       [&]() {   // this warp is done with raw[hh]; the last of the 8 re-arms the TMA (same half, next tile)
+                           __syncwarp();
+                           if (lane == 0) {
+                               __threadfence_block();
+                               const uint32_t old = atomicAdd(raw_readers + hh, 1u);
+                               if (old == kTeamWarps - 1) {
+                                   raw_readers[hh] = 0;
                                    __threadfence_block();
-                                   const uint32_t old = atomicAdd(raw_readers, 1u);
-                                   if (old == kTeamWarps - 1) {
-                                       *raw_readers = 0;
-                                       __threadfence_block();
-                                       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                                       if (nt.valid) tile_issue_tma(a, nt.cc, nt.tile, raw, bar_raw);
-                                   }
+                                   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                                   if (nt.valid) half_issue_tma(a, nt.cc, nt.tile, hh, rawb, bar_raw0 + 8 * hh);
                                }
                            }
                        },
-                       [&]() {   // stage 2 of the previous tile must have read Y
-                           if (pass == 0 && tnum > 0) mbar_wait(bar_yfree, (tnum - 1) & 1);
+                       [&]() {   // stage 2 of the previous tile must have read Y[hh]
+                           if (tnum > 0) mbar_wait(bar_yfree0 + 8 * hh, (tnum - 1) & 1);
                        });
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_yfull0 + 8 * hh);
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_yfull);
             cur = nt;
         }
     } else {
         // ========================= team B: stage 2, mel, clip max, output (consumer of Y) ======================
         const int bw = warp - kTeamWarps;                       // 0..7, scheduler bw & 3
-        // Stage-2 slots of this warp: bw and bw + 8 (13 slots: warps 0..4 run two, 5..7 one); the warps
-        // with one slot take three of the 16 mel runs, the others one or two, so the team is balanced.
-        const int n_slots = bw + kTeamWarps < fft::kNumSlots ? 2 : 1;
-        const int n_runs = bw >= 5 ? 3 : ((bw & 3) == 0 ? 2 : 1);
-        auto run_of = [&](int i) { return bw >= 5 ? bw + 4 * i : (i == 0 ? bw : bw + 8); };   // 5:{5,9,13} 0:{0,8} 4:{4,12}
-        // TMEM windows (128 columns each, 4 per lane quarter): quarter q = bw & 3 hosts warp q (first) and q + 4
-        const int win0 = bw < 4 ? 0 : ((bw & 3) == 0 ? 2 : 1);
+        // Warps 0..6 run stage 2 (two k2 slots each).  The 16 mel runs: two per warp of a lane quarter pair
+        // (q, q+4), except quarter 3 where warp 7 (no stage 2) takes three and warp 3 one.
+        const bool s2 = bw < kStage2Warps;
+        const Stage2Lane L = stage2_lane_setup(kt, s2 ? bw : 0, lane);
+        const int n_runs = bw == 7 ? 3 : (bw == 3 ? 1 : 2);
+        auto run_of = [&](int i) { return bw == 7 ? 7 + 4 * i : (i == 0 ? bw : bw + 8); };   // 7:{7,11,15} 3:{3} b:{b,b+8}
+        // TMEM windows (128 columns each, 4 per lane quarter): quarter bw & 3, warp q first, then warp q + 4
+        const int win0 = bw < 4 ? 0 : (bw == 7 ? 1 : 2);
         const uint32_t tquart = tmem_base + (static_cast<uint32_t>((bw & 3) * 32) << 16);
 
         Step cur = first_step_of_clip(cluster_id);
@@ -677,7 +711,7 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
                 const float floor_v = fmaxf(gmax - 8.0f, -10.0f);     // TF-FE:158 (log-mel is never below -10)
                 if (rank == 0 && bw == 0 && lane == 0 && a.gmax) a.gmax[pend_b] = gmax;
 
-                // single pass: TMEM -> (max(log10, gmax-8)+4)/4 -> HBM
+                // single pass: TMEM -> (max(log10, gmax-8)+4)/4 -> HBM (one float2 = two adjacent frames per lane)
                 tmem_wait_st();
                 constexpr float kLog10_2 = 0.30102999566398120f;
                 const float silent = (floor_v + 4.0f) * 0.25f;
@@ -690,9 +724,8 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
                         float r[16];
                         tmem_ld_x16(twin + j * kTmemColsPerTile, r);
                         const int f0 = (rank + j * kCluster) * kTile;
-                        const int fa = f0 + pair_frame_a(lane);
                         float* of = ob + f0;
-                        const bool va = fa < kNFrames, vb = fa + 16 < kNFrames;
+                        const bool va = f0 + pair_frame_a(lane) < kNFrames;    // 3000 is even: both frames or none
 #define WLM_OUT_ROW(q)                                                                                         \
     case (q) + 1: {                                                                                            \
         float2 lg = __fmul2_rn(make_float2(lg2_approx(r[2 * (q)]), lg2_approx(r[2 * (q) + 1])),                \
@@ -700,8 +733,7 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
         lg.x = fmaxf(lg.x, floor_v);                                                                           \
         lg.y = fmaxf(lg.y, floor_v);                                                                           \
         lg = __ffma2_rn(lg, make_float2(0.25f, 0.25f), make_float2(1.0f, 1.0f)); /* (x+4)/4, TF-FE:161 */       \
-        if (va) of[(q) * kNFrames] = lg.x;                                                                     \
-        if (vb) of[(q) * kNFrames + 16] = lg.y;                                                                \
+        if (va) *reinterpret_cast<float2*>(of + (q) * kNFrames) = lg;                                          \
     }
                         switch (nf) {   // fall-through: exactly nf rows, static register indices
                             WLM_OUT_ROW(7) WLM_OUT_ROW(6) WLM_OUT_ROW(5) WLM_OUT_ROW(4)
@@ -712,12 +744,9 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
                     }
                     // tiles of mine that hold no real sample: log-mel is exactly -10 everywhere
                     for (int tile = rank + pend_n_my * kCluster; tile < kTilesPerClip; tile += kCluster) {
-                        const int fa = tile * kTile + pair_frame_a(lane);
                         float* of = ob + tile * kTile;
-                        for (int q = 0; q < nf; ++q) {
-                            if (fa < kNFrames) of[q * kNFrames] = silent;
-                            if (fa + 16 < kNFrames) of[q * kNFrames + 16] = silent;
-                        }
+                        if (tile * kTile + pair_frame_a(lane) < kNFrames)
+                            for (int q = 0; q < nf; ++q) *reinterpret_cast<float2*>(of + q * kNFrames) = make_float2(silent, silent);
                     }
                 }
                 pend = false;
@@ -736,9 +765,10 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
                     m2.x = fmaxf(m2.x, r2.x);
                     m2.y = fmaxf(m2.y, r2.y);
                 }
-                const int fa = prev.tile * kTile + pair_frame_a(lane);     // frames past 3000 do not exist
-                if (fa < kNFrames) mx.x = fmaxf(mx.x, m2.x);
-                if (fa + 16 < kNFrames) mx.y = fmaxf(mx.y, m2.y);
+                if (prev.tile * kTile + pair_frame_a(lane) < kNFrames) {     // frames past 3000 do not exist
+                    mx.x = fmaxf(mx.x, m2.x);
+                    mx.y = fmaxf(mx.y, m2.y);
+                }
                 if (clip_ends) {
                     float v = fmaxf(mx.x, mx.y);
 #pragma unroll
@@ -751,7 +781,7 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
             }
             // ---- D: the clip ended: deliver the CTA's max to every CTA of the cluster (DSMEM) ---------------------
             if (clip_ends) {
-                if (bw == 0) {
+                if (bw == 7) {   // the warp without stage-2 work
                     if (mel_tile) mbar_wait(bar_pfree, prev_tnum & 1);   // every warp's warp_max is visible
                     float c = (mel_tile && lane < kTeamWarps) ? warp_max[cpar * 8 + lane] : 0.f;
 #pragma unroll
@@ -772,20 +802,18 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
                 pend_ord = clip_ord;
                 ++clip_ord;
             }
-            // ---- C: stage 2 --------------------------------------------------------------------------------
-            if (do_tile) {
-                mbar_wait(bar_yfull, tnum & 1);
+            // ---- C: stage 2, both halves ---------------------------------------------------------------------
+            if (do_tile && s2) {
 #pragma unroll 1
-                for (int i = 0; i < n_slots; ++i) {
-                    stage2(kt, Y, P, bw + i * kTeamWarps, lane,
+                for (int hh = 0; hh < 2; ++hh) {
+                    mbar_wait(bar_yfull0 + 8 * hh, tnum & 1);
+                    stage2(L, bw == 0, Y + hh * kYFloat2, P, hh, lane,
                            [&]() {
-                               if (i == n_slots - 1) {
-                                   __syncwarp();
-                                   if (lane == 0) mbar_arrive(bar_yfree);   // phase tnum
-                               }
+                               __syncwarp();
+                               if (lane == 0) mbar_arrive(bar_yfree0 + 8 * hh);   // phase tnum
                            },
                            [&]() {   // the mel stage of the previous tile must have read P (all 8 warps)
-                               if (i == 0 && tnum > 0) mbar_wait(bar_pfree, (tnum - 1) & 1);
+                               if (hh == 0 && tnum > 0) mbar_wait(bar_pfree, (tnum - 1) & 1);
                            });
                 }
                 __syncwarp();
