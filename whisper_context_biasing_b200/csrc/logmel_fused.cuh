@@ -50,25 +50,20 @@ using fused::vadd; using fused::vsub; using fused::vmul; using fused::vfma; usin
 namespace wlm {
 namespace fused {
 
-constexpr int kTile = 64;                 // frames per tile (unit of the mel stage, TMEM slot, output pass)
-constexpr int kHalf = 32;                 // frames per half tile (unit of TMA, stage 1 and stage 2)
+constexpr int kTile = 64;                 // frames per tile
 constexpr int kWarps = 16;
-constexpr int kTeamWarps = 8;             // warps 0..7: TMA + stage 1; warps 8..15: stage 2, mel, output
-constexpr int kStage2Warps = 7;           // 13 k2 slots, two per warp (lanes 0-15 / 16-31)
 constexpr int kThreads = kWarps * 32;
 constexpr int kTilesPerClip = (kNFrames + kTile - 1) / kTile;  // 47
-// raw PCM of a half tile: two regions of 16 frames each, 2800 samples = 16 (mod 32): 16 banks apart
-constexpr int kRegion = 15 * kHop + kNfft;                     // 2800 samples: frames 0..15 of a half tile
-constexpr int kRegionStep = 16 * kHop;                         // 2560: region B starts 16 frames later
-constexpr int kRawFloats = 2 * kRegion;                        // 5600 per buffer
-constexpr int kHalfSamples = 31 * kHop + kNfft;                // 5360
-constexpr int kYStride = 401;                                  // float2 per n1 row (25 comps x 16 pairs + 1: odd)
-constexpr int kYFloat2 = 16 * kYStride;                        // per buffer
+constexpr int kRegion = 31 * kHop + kNfft;                     // 5360 samples: frames 0..31 of a half tile
+constexpr int kRegionStep = 32 * kHop;                         // 5120: region B starts 32 frames later
+constexpr int kRawFloats = 2 * kRegion;                        // 10720 (5360 = 16 mod 32: regions 16 banks apart)
+constexpr int kTileSamples = 63 * kHop + kNfft;                // 10480
+constexpr int kYStride = 801;                                  // float2 per n1 row (25*32 + 1: odd)
+constexpr int kYFloat2 = 16 * kYStride;
 constexpr int kPFloat2 = kNFreq * 32;
-static_assert(kRegion % 32 == 16, "the two raw regions must sit 16 banks apart");
 
-constexpr int kSmemRaw = 2 * kRawFloats * 4;    // 44,800  (double buffered)
-constexpr int kSmemY = 2 * kYFloat2 * 8;        // 102,656 (double buffered)
+constexpr int kSmemRaw = kRawFloats * 4;        // 42,880
+constexpr int kSmemY = kYFloat2 * 8;            // 102,528
 constexpr int kSmemP = kPFloat2 * 8;            // 51,456
 constexpr int kSmemBytes = kSmemRaw + kSmemY + kSmemP + 256;
 
@@ -255,12 +250,11 @@ __device__ __forceinline__ ClipCtx clip_ctx(const ClipArgs& a, int b) {
     c.n_act = min(kTilesPerClip, (c.len + kNfft / 2 + kTile * kHop - 1) / (kTile * kHop));
     return c;
 }
-// first sample (clip coordinates, may be negative) of half `hh` of tile `tile`
-__device__ __forceinline__ int half_s0(int tile, int hh) { return (tile * kTile + hh * kHalf) * kHop - kNfft / 2; }
+__device__ __forceinline__ int tile_s0(int tile) { return tile * (kTile * kHop) - kNfft / 2; }
 
-// issued by one thread: both regions of the half tile, valid sample range only
-__device__ __forceinline__ void half_issue_tma(const ClipArgs& a, const ClipCtx& c, int tile, int hh, float* raw, uint32_t bar) {
-    const int s0 = half_s0(tile, hh);
+// issued by one thread: both regions of the tile, valid sample range only
+__device__ __forceinline__ void tile_issue_tma(const ClipArgs& a, const ClipCtx& c, int tile, float* raw, uint32_t bar) {
+    const int s0 = tile_s0(tile);
     const int esz = a.pcm_format == WLM_PCM_I16 ? 2 : 4;
     const int gran = 16 / esz;
     const int len_up = min((c.len + gran - 1) / gran * gran, kNSamples);
@@ -274,7 +268,7 @@ __device__ __forceinline__ void half_issue_tma(const ClipArgs& a, const ClipCtx&
         n[r] = max(hi - lo[r], 0);
         total += static_cast<uint32_t>(n[r]) * esz;
     }
-    mbar_expect_tx(bar, total);      // (total may be 0 for a half that lies past the clip: completes at once)
+    mbar_expect_tx(bar, total);
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
         if (n[r] <= 0) continue;
@@ -288,34 +282,30 @@ __device__ __forceinline__ void half_issue_tma(const ClipArgs& a, const ClipCtx&
 }
 
 // int16 -> float32 expansion in place (staging sits in the byte range of region B) + reflect /
-// zero-fill patching of every position outside [0, len).  Only edge halves and int16 input pay.
-// Executed by the 256 threads of the stage-1 team (named barrier 1).
-constexpr int kTeamThreads = 256;
-__device__ __forceinline__ void team_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
-
-__device__ __forceinline__ void half_fixup(const ClipArgs& a, const ClipCtx& c, int tile, int hh, float* raw, int tid) {
-    const int s0 = half_s0(tile, hh);
+// zero-fill patching of every position outside [0, len).  Only edge tiles and int16 input pay.
+__device__ __forceinline__ void tile_fixup(const ClipArgs& a, const ClipCtx& c, int tile, float* raw) {
+    const int tid = threadIdx.x;
+    const int s0 = tile_s0(tile);
     if (a.pcm_format == WLM_PCM_I16) {
         const int16_t* st = reinterpret_cast<const int16_t*>(raw + kRegion);
         constexpr float kScale = 1.0f / 32768.0f;
-        constexpr int kPer = (kRegion + kTeamThreads - 1) / kTeamThreads;
-        for (int i = tid; i < kRegion; i += kTeamThreads) raw[i] = static_cast<float>(st[i]) * kScale;
-        float tmp[kPer];
+        for (int i = tid; i < kRegion; i += kThreads) raw[i] = static_cast<float>(st[i]) * kScale;
+        float tmp[(kRegion + kThreads - 1) / kThreads];
 #pragma unroll
-        for (int j = 0; j < kPer; ++j) {
-            const int i = tid + j * kTeamThreads;
+        for (int j = 0; j < (kRegion + kThreads - 1) / kThreads; ++j) {
+            const int i = tid + j * kThreads;
             tmp[j] = i < kRegion ? static_cast<float>(st[kRegion + i]) * kScale : 0.f;
         }
-        team_sync();
+        __syncthreads();
 #pragma unroll
-        for (int j = 0; j < kPer; ++j) {
-            const int i = tid + j * kTeamThreads;
+        for (int j = 0; j < (kRegion + kThreads - 1) / kThreads; ++j) {
+            const int i = tid + j * kThreads;
             if (i < kRegion) raw[kRegion + i] = tmp[j];
         }
-        team_sync();
+        __syncthreads();
     }
-    if (s0 < 0 || s0 + kHalfSamples > c.len) {
-        for (int idx = tid; idx < kRawFloats; idx += kTeamThreads) {
+    if (s0 < 0 || s0 + kTileSamples > c.len) {
+        for (int idx = tid; idx < kRawFloats; idx += kThreads) {
             const int r = idx >= kRegion ? 1 : 0;
             const int s = s0 + r * kRegionStep + (idx - r * kRegion);
             if (s >= 0 && s < c.len) continue;
@@ -324,98 +314,74 @@ __device__ __forceinline__ void half_fixup(const ClipArgs& a, const ClipCtx& c, 
             float v = 0.f;
             if (sr >= 0 && sr < c.len) {
                 const int u = sr - s0;
-                if (u >= 0 && u < kHalfSamples) v = raw[u < kRegion ? u : kRegion + (u - kRegionStep)];
+                if (u >= 0 && u < kTileSamples) v = raw[u < kRegion ? u : kRegion + (u - kRegionStep)];
             }
             raw[idx] = v;
         }
-        team_sync();
+        __syncthreads();
     }
 }
 
 // ---- stage 1 ----------------------------------------------------------------------------------
-// Half tile of 32 frames = 16 pairs of adjacent frames (2p, 2p+1).  Team warp a (0..7), lane
-// (n1 = lane & 15, g = lane >> 4): pair p = a + 8 g, i.e. frames 2a, 2a+1 of region g.
+// warp w, lane (n1 = lane & 15, g = lane >> 4): frames (32 g + w, 32 g + w + 16) of the tile.
 // `loaded()` runs once the warp no longer needs the raw buffer, `before_store()` just before Y is written.
 template <class Loaded, class BeforeStore>
-__device__ __forceinline__ void stage1(const float* raw, float2* Y, const float (&wv)[25], int tw, int a, int lane,
+__device__ __forceinline__ void stage1(const float* raw, float2* Y, const float (&wv)[25], int tw, int warp, int lane,
                                        Loaded loaded, BeforeStore before_store) {
     const int n1 = lane & 15, g = lane >> 4;
-    const float* p0 = raw + g * kRegion + 2 * kHop * a + 25 * n1;
+    const float* p0 = raw + g * kRegion + kHop * warp + 25 * n1;
     const float* p1 = p0 - kNfft;
     V2 y[25];
 #pragma unroll
     for (int t = 0; t < 25; ++t) {
         const float* p = (t >= tw) ? p1 : p0;
-        const float xa = p[16 * t], xb = p[16 * t + kHop];
+        const float xa = p[16 * t], xb = p[16 * t + 16 * kHop];
         y[t] = mk(xa * wv[t], xb * wv[t]);
     }
     loaded();      // (fence inside: every LDS above has been performed)
     V2 out[25];
     fft::rfft25<V2>(y, out);
     before_store();
-    float2* yo = Y + n1 * kYStride + (a + 8 * g);
+    float2* yo = Y + n1 * kYStride + (warp + 16 * g);
 #pragma unroll
-    for (int c = 0; c < 25; ++c) yo[c * 16] = out[c].v;
+    for (int c = 0; c < 25; ++c) yo[c * 32] = out[c].v;
 }
 
 // ---- stage 2 ----------------------------------------------------------------------------------
-// One warp = two k2 slots x 16 frame pairs: lane = (pair = lane & 15, which slot = lane >> 4).  The slot
-// only selects per-lane offsets (component inside Y, output bins inside P), so all 7 warps run the
-// same instructions (a 13-way templated version thrashed the instruction cache).
-struct Stage2Lane {
-    int comp_off;        // float2 offset of the slot's real component inside a Y row (comp * 16)
-    bool real, active;   // k2 = 0 slot (no imaginary part) / lane has a slot at all
-    uint32_t pbin[8];    // 16 x 16-bit: P row offset (bin * 32) of cfft16 output i, two per register
-};
-__device__ __forceinline__ Stage2Lane stage2_lane_setup(const KernelTables& kt, int bw, int lane) {
-    Stage2Lane L;
-    const int slot = 2 * bw + (lane >> 4);
-    L.active = slot < fft::kNumSlots;
-    const int sl = L.active ? slot : fft::kNumSlots - 1;
-    L.real = sl == 0;
-    L.comp_off = kt.slot_comp_off[sl] / 2;      // table holds comp * 32
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-        L.pbin[i] = static_cast<uint32_t>(static_cast<uint16_t>(kt.slot_pbin_off[sl][2 * i])) |
-                    (static_cast<uint32_t>(static_cast<uint16_t>(kt.slot_pbin_off[sl][2 * i + 1])) << 16);
-    return L;
-}
-
+// warp = k2 slot (uniform), lane = frame pair.  One code path for all 13 slots: the slot only selects
+// table offsets, so every warp runs the same instructions (a 13-way templated version thrashed the
+// instruction cache: 28 % of issue stalls were "no instruction").
 // `loaded()` runs once Y has been read, `before_store()` just before P is written.
 template <class Loaded, class BeforeStore>
-__device__ __forceinline__ void stage2(const Stage2Lane& L, bool warp_has_real, const float2* Y, float2* P, int hh, int lane,
+__device__ __forceinline__ void stage2(const KernelTables& kt, const float2* Y, float2* P, int slot, int lane,
                                        Loaded loaded, BeforeStore before_store) {
-    const float2* yl = Y + L.comp_off + (lane & 15);
+    const float2* yl = Y + kt.slot_comp_off[slot] + lane;
     V2 xr[16], xi[16];
 #pragma unroll
-    for (int n1 = 0; n1 < 16; ++n1) {
-        xr[n1].v = yl[n1 * kYStride];
-        xi[n1].v = yl[n1 * kYStride + 16];
-    }
-    loaded();      // (mbarrier.arrive is a release: the loads above are ordered before it)
-    if (warp_has_real) {   // k2 = 0: Y is purely real; the "imaginary" load fetched the next component
+    for (int n1 = 0; n1 < 16; ++n1) xr[n1].v = yl[n1 * kYStride];
+    if (slot != 0) {
 #pragma unroll
-        for (int n1 = 0; n1 < 16; ++n1)
-            if (L.real) xi[n1] = mk(0.f, 0.f);
+        for (int n1 = 0; n1 < 16; ++n1) xi[n1].v = yl[n1 * kYStride + 32];
+    } else {  // k2 = 0: Y is purely real
+#pragma unroll
+        for (int n1 = 0; n1 < 16; ++n1) xi[n1] = mk(0.f, 0.f);
     }
     fft::cfft16<V2>(xr, xi);
     V2 pw[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) pw[i] = vfma(xr[i], xr[i], vmul(xi[i], xi[i]));
+    loaded();
     before_store();
-    if (L.active) {
-        float2* pl = P + 16 * hh + (lane & 15);
+    float2* pl = P + lane;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            // slot 0 writes bins 25 j twice (k1 and 16-k1 are conjugates): same thread, same value class
-            const uint32_t off = (i & 1) ? (L.pbin[i >> 1] >> 16) : (L.pbin[i >> 1] & 0xffffu);
-            pl[off] = pw[i].v;
-        }
+    for (int i = 0; i < 16; ++i) {
+        // slot 0 writes bins 25 j twice (k1 and 16-k1 are conjugates): same thread, same value class
+        pl[kt.slot_pbin_off[slot][i]] = pw[i].v;
     }
 }
 
-// lane = frame pair of the tile: frames (2 lane, 2 lane + 1)
-__device__ __forceinline__ int pair_frame_a(int lane) { return 2 * lane; }
+// lane = frame pair: frames (lane, lane+16) for lane < 16, (lane+16, lane+32) for lane >= 16
+__device__ __forceinline__ int pair_frame_a(int lane) { return lane < 16 ? lane : lane + 16; }
 
 // ---- mel stage ------------------------------------------------------------------------------------
 // One warp, its run of <= 8 filters, 32 frame pairs.  Groups of bins between adjacent filter centres
@@ -549,21 +515,21 @@ __global__ void __launch_bounds__(kThreads, 1)
 logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt, const float* __restrict__ win_lane) {
     namespace cg = cooperative_groups;
     extern __shared__ __align__(128) unsigned char smem[];
-    float* raw = reinterpret_cast<float*>(smem);                                   // [2][kRawFloats]
-    float2* Y = reinterpret_cast<float2*>(smem + kSmemRaw);                       // [2][kYFloat2]
-    float2* P = reinterpret_cast<float2*>(smem + kSmemRaw + kSmemY);              // [201][32]
+    float* raw = reinterpret_cast<float*>(smem);
+    float2* Y = reinterpret_cast<float2*>(smem + kSmemRaw);
+    float2* P = reinterpret_cast<float2*>(smem + kSmemRaw + kSmemY);
     unsigned char* misc = smem + kSmemRaw + kSmemY + kSmemP;
-    // mbarriers (8 B each).  No CTA-wide barrier in steady state: every hand-over is one of these.
-    const uint32_t bar_raw0 = smem_u32(misc);         // [2] TMA landed the half tile's PCM              (tx, 1 arrival)
-    const uint32_t bar_yfull0 = smem_u32(misc + 16);  // [2] the 8 stage-1 warps stored their output       (8)
-    const uint32_t bar_yfree0 = smem_u32(misc + 32);  // [2] the 7 stage-2 warps have read Y               (7)
-    const uint32_t bar_pfull = smem_u32(misc + 48);   //     the 7 stage-2 warps stored both halves' power (7)
-    const uint32_t bar_pfree = smem_u32(misc + 56);   //     the 8 team-B warps finished the mel stage     (8)
-    const uint32_t bar_clip0 = smem_u32(misc + 64);   // [2] every CTA of the cluster delivered its max    (kCluster)
-    uint32_t* raw_readers = reinterpret_cast<uint32_t*>(misc + 80);   // [2] stage-1 warps done with raw buffer i
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 88);     // TMEM base address
-    float* warp_max = reinterpret_cast<float*>(misc + 96);            // [2][8] (clip parity)
-    float* clip_max = reinterpret_cast<float*>(misc + 160);           // [2][8]: written by the PEERS (DSMEM)
+    // mbarriers (8 B each).  No CTA-wide barrier separates the stages of a tile: every hand-over between
+    // warps is one of these, so warps drift apart and FMA-bound, load-bound and idle phases overlap.
+    const uint32_t bar_raw = smem_u32(misc);         // TMA landed the tile's PCM            (tx, 1 arrival)
+    const uint32_t bar_yfull = smem_u32(misc + 8);   // all 16 warps stored stage-1 output    (16)
+    const uint32_t bar_yfree = smem_u32(misc + 16);  // all 13 stage-2 warps have read Y      (13)
+    const uint32_t bar_pfull = smem_u32(misc + 24);  // all 13 stage-2 warps stored the power (13)
+    const uint32_t bar_pfree = smem_u32(misc + 32);  // all 16 warps finished the mel stage   (16)
+    uint32_t* raw_readers = reinterpret_cast<uint32_t*>(misc + 40);   // warps done with the raw buffer
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 48);     // TMEM base address
+    float* warp_max = reinterpret_cast<float*>(misc + 64);            // [2][16] (clip parity)
+    float* cta_max = reinterpret_cast<float*>(misc + 192);            // [2] (clip parity), read by the peers
 
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = static_cast<int>(cluster.block_rank());
@@ -573,27 +539,38 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler
     if (tid == 0) {
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(bar_raw0 + 8 * i, 1);
-            mbar_init(bar_yfull0 + 8 * i, kTeamWarps);
-            mbar_init(bar_yfree0 + 8 * i, kStage2Warps);
-            mbar_init(bar_clip0 + 8 * i, kCluster);
-            raw_readers[i] = 0;
-        }
-        mbar_init(bar_pfull, kStage2Warps);
-        mbar_init(bar_pfree, kTeamWarps);
+        mbar_init(bar_raw, 1);
+        mbar_init(bar_yfull, kWarps);
+        mbar_init(bar_yfree, fft::kNumSlots);
+        mbar_init(bar_pfull, fft::kNumSlots);
+        mbar_init(bar_pfree, kWarps);
+        *raw_readers = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) tmem_alloc_512(smem_u32(tmem_slot));
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    cluster.sync();          // every CTA's barriers exist before a peer may arrive on them
+    __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    // this warp's TMEM window: lane quarter (warp & 3), 96 columns at (warp >> 2) * 96
+    const uint32_t twin = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) +
+                          static_cast<uint32_t>((warp >> 2) * kTmemColsPerWarp);
+
+    // per-lane stage-1 constants
+    const int n1 = lane & 15;
+    float wv[25];
+#pragma unroll
+    for (int t = 0; t < 25; ++t) wv[t] = win_lane[n1 * 25 + t];
+    const int tw = n1 == 0 ? 25 : (kNfft - 25 * n1 + 15) / 16;
 
     // The CTA's work is a stream of steps, one per tile it owns (a clip in which it owns no active
-    // tile still contributes one empty step so that it delivers a max for that clip).  A tile is two
-    // half tiles; half h of the CTA's n-th tile uses buffer h (raw and Y) and phase n (parity n & 1)
-    // of the per-buffer barriers; the per-tile barriers (P full / P free) use phase n as well.
+    // tile still contributes one empty step so that it takes part in that clip's cluster barrier).
+    // Program order of every warp in step i (tile t_i):
+    //   A  stage 1 of t_i            wait raw | load | last warp re-arms TMA | FFT | wait Y free | store | arrive Y full
+    //   F  output pass of the clip that ended one step ago   (cluster barrier WAIT, TMEM read-back, stores)
+    //   B  mel stage of t_{i-1}      wait P full | ... | arrive P free
+    //   D  if t_{i-1} ended a clip:  wait P free | CTA max -> cta_max | cluster barrier ARRIVE
+    //   C  stage 2 of t_i (13 warps) wait Y full | load | arrive Y free | FFT | wait P free | store | arrive P full
     struct Step {
         bool valid, has_tile, last;
         int j, n_my, tile;
@@ -632,100 +609,76 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
         return s;
     };
 
-    if (warp < kTeamWarps) {
-        // ========================= team A: TMA + stage 1 (producer of Y) ===================================
-        const int n1 = lane & 15;
-        float wv[25];
-#pragma unroll
-        for (int t = 0; t < 25; ++t) wv[t] = win_lane[n1 * 25 + t];
-        const int tw = n1 == 0 ? 25 : (kNfft - 25 * n1 + 15) / 16;
+    // Phase bookkeeping: the n-th tile this CTA processes (n = 0, 1, ...) uses phase n of every barrier,
+    // i.e. parity n & 1.  A wait for phase n is only issued by a warp that has already arrived on phase n
+    // or whose own later work is needed to complete phase n+1, so the barrier is never more than one
+    // phase ahead of a waiter.
+    int fin_parity = 0;                      // parity of the clip whose max is exchanged next
+    Step cur = first_step_of_clip(cluster_id);
+    Step prev = cur;
+    prev.valid = false;
+    int tnum = 0, prev_tnum = 0;             // ordinal of cur's / prev's tile among the tiles of this CTA
+    if (tid == 0) {
+        Step f = cur;
+        if (f.valid && !f.has_tile) f = next_tile_step(f);
+        if (f.valid) tile_issue_tma(a, f.cc, f.tile, raw, bar_raw);
+    }
+    float2 mx = make_float2(0.f, 0.f);       // running max of the mel power of the clip in flight (>= 0)
+    bool pend = false;                       // an output pass is owed (cluster barrier arrived, not yet waited)
+    int pend_b = 0, pend_n_my = 0;
 
-        Step cur = first_step_of_clip(cluster_id);
-        if (cur.valid && !cur.has_tile) cur = next_tile_step(cur);
-        if (tid == 0 && cur.valid) {
-            half_issue_tma(a, cur.cc, cur.tile, 0, raw, bar_raw0);
-            half_issue_tma(a, cur.cc, cur.tile, 1, raw + kRawFloats, bar_raw0 + 8);
-        }
-        for (int tnum = 0; cur.valid; ++tnum) {
+    while (cur.valid || prev.valid || pend) {
+        const bool do_tile = cur.valid && cur.has_tile;
+        // ---- A: stage 1 ----------------------------------------------------------------------------
+        if (do_tile) {
+            mbar_wait(bar_raw, tnum & 1);
+            tile_fixup(a, cur.cc, cur.tile, raw);
             const Step nt = next_tile_step(cur);
-#pragma unroll 1
-            for (int hh = 0; hh < 2; ++hh) {
-                float* rawb = raw + hh * kRawFloats;
-                mbar_wait(bar_raw0 + 8 * hh, tnum & 1);
-                half_fixup(a, cur.cc, cur.tile, hh, rawb, tid);
-                stage1(rawb, Y + hh * kYFloat2, wv, tw, warp, lane,
-                       [&]() {   // this warp is done with raw[hh]; the last of the 8 re-arms the TMA (same half, next tile)
-                           __syncwarp();
-                           if (lane == 0) {
+            stage1(raw, Y, wv, tw, warp, lane,
+                   [&]() {   // this warp is done with raw: the last of the 16 re-arms the TMA for the next tile
+                       __syncwarp();
+                       if (lane == 0) {
+                           __threadfence_block();
+                           const uint32_t old = atomicAdd(raw_readers, 1u);
+                           if (old == kWarps - 1) {
+                               *raw_readers = 0;
                                __threadfence_block();
-                               const uint32_t old = atomicAdd(raw_readers + hh, 1u);
-                               if (old == kTeamWarps - 1) {
-                                   raw_readers[hh] = 0;
-                                   __threadfence_block();
-                                   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                                   if (nt.valid) half_issue_tma(a, nt.cc, nt.tile, hh, rawb, bar_raw0 + 8 * hh);
-                               }
+                               asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                               if (nt.valid) tile_issue_tma(a, nt.cc, nt.tile, raw, bar_raw);
                            }
-                       },
-                       [&]() {   // stage 2 of the previous tile must have read Y[hh]
-                           if (tnum > 0) mbar_wait(bar_yfree0 + 8 * hh, (tnum - 1) & 1);
-                       });
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_yfull0 + 8 * hh);
-            }
-            cur = nt;
+                       }
+                   },
+                   [&]() {   // stage 2 of the previous tile must have read Y
+                       if (tnum > 0) mbar_wait(bar_yfree, (tnum - 1) & 1);
+                   });
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_yfull);
         }
-    } else {
-        // ========================= team B: stage 2, mel, clip max, output (consumer of Y) ======================
-        const int bw = warp - kTeamWarps;                       // 0..7, scheduler bw & 3
-        // Warps 0..6 run stage 2 (two k2 slots each).  The 16 mel runs: two per warp of a lane quarter pair
-        // (q, q+4), except quarter 3 where warp 7 (no stage 2) takes three and warp 3 one.
-        const bool s2 = bw < kStage2Warps;
-        const Stage2Lane L = stage2_lane_setup(kt, s2 ? bw : 0, lane);
-        const int n_runs = bw == 7 ? 3 : (bw == 3 ? 1 : 2);
-        auto run_of = [&](int i) { return bw == 7 ? 7 + 4 * i : (i == 0 ? bw : bw + 8); };   // 7:{7,11,15} 3:{3} b:{b,b+8}
-        // TMEM windows (128 columns each, 4 per lane quarter): quarter bw & 3, warp q first, then warp q + 4
-        const int win0 = bw < 4 ? 0 : (bw == 7 ? 1 : 2);
-        const uint32_t tquart = tmem_base + (static_cast<uint32_t>((bw & 3) * 32) << 16);
-
-        Step cur = first_step_of_clip(cluster_id);
-        Step prev = cur;
-        prev.valid = false;
-        int tnum = 0, prev_tnum = 0;         // ordinal of cur's / prev's tile among the tiles of this CTA
-        int clip_ord = 0;                    // ordinal of the clip whose max is exchanged next
-        float2 mx = make_float2(0.f, 0.f);   // running max of the mel power of the clip in flight (>= 0)
-        bool pend = false;                   // an output pass is owed (max delivered, peers not yet awaited)
-        int pend_b = 0, pend_n_my = 0, pend_ord = 0;
-
-        while (cur.valid || prev.valid || pend) {
-            const bool do_tile = cur.valid && cur.has_tile;
-            // ---- F: output pass of the clip that ended one step ago ---------------------------------------
-            if (pend) {
-                const int par = pend_ord & 1;
-                mbar_wait(bar_clip0 + 8 * par, (pend_ord >> 1) & 1);
-                float pmax = lane < kCluster ? clip_max[par * 8 + lane] : 0.f;
+        // ---- F: output pass of the clip that ended one step ago -----------------------------------------
+        if (pend) {
+            asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+            float pmax = 0.f;
+            if (lane < kCluster) pmax = *cluster.map_shared_rank(cta_max + fin_parity, lane);
 #pragma unroll
-                for (int o = 4; o > 0; o >>= 1) pmax = fmaxf(pmax, __shfl_xor_sync(0xffffffffu, pmax, o));
-                pmax = __shfl_sync(0xffffffffu, pmax, 0);
-                const float gmax = log10_floor(pmax);                 // TF-FE:157
-                const float floor_v = fmaxf(gmax - 8.0f, -10.0f);     // TF-FE:158 (log-mel is never below -10)
-                if (rank == 0 && bw == 0 && lane == 0 && a.gmax) a.gmax[pend_b] = gmax;
+            for (int o = 4; o > 0; o >>= 1) pmax = fmaxf(pmax, __shfl_xor_sync(0xffffffffu, pmax, o));
+            pmax = __shfl_sync(0xffffffffu, pmax, 0);
+            fin_parity ^= 1;
+            const float gmax = log10_floor(pmax);                 // TF-FE:157
+            const float floor_v = fmaxf(gmax - 8.0f, -10.0f);     // TF-FE:158 (log-mel is never below -10)
+            if (rank == 0 && tid == 0 && a.gmax) a.gmax[pend_b] = gmax;
 
-                // single pass: TMEM -> (max(log10, gmax-8)+4)/4 -> HBM (one float2 = two adjacent frames per lane)
-                tmem_wait_st();
-                constexpr float kLog10_2 = 0.30102999566398120f;
-                const float silent = (floor_v + 4.0f) * 0.25f;
-                for (int i = 0; i < n_runs; ++i) {
-                    const int run = run_of(i);
-                    const int nf = kt.nf[run];
-                    const uint32_t twin = tquart + static_cast<uint32_t>((win0 + i) * kTmemColsPerWarp);
-                    float* ob = a.out + (static_cast<int64_t>(pend_b) * a.n_mels + kt.m0[run]) * kNFrames + pair_frame_a(lane);
-                    for (int j = 0; j < pend_n_my; ++j) {
-                        float r[16];
-                        tmem_ld_x16(twin + j * kTmemColsPerTile, r);
-                        const int f0 = (rank + j * kCluster) * kTile;
-                        float* of = ob + f0;
-                        const bool va = f0 + pair_frame_a(lane) < kNFrames;    // 3000 is even: both frames or none
+            // single pass: TMEM -> (max(log10, gmax-8)+4)/4 -> HBM
+            tmem_wait_st();
+            constexpr float kLog10_2 = 0.30102999566398120f;
+            const int nf = kt.nf[warp];
+            float* ob = a.out + (static_cast<int64_t>(pend_b) * a.n_mels + kt.m0[warp]) * kNFrames + pair_frame_a(lane);
+            for (int j = 0; j < pend_n_my; ++j) {
+                float r[16];
+                tmem_ld_x16(twin + j * kTmemColsPerTile, r);
+                const int f0 = (rank + j * kCluster) * kTile;
+                const int fa = f0 + pair_frame_a(lane);
+                float* of = ob + f0;
+                const bool va = fa < kNFrames, vb = fa + 16 < kNFrames;
 #define WLM_OUT_ROW(q)                                                                                         \
     case (q) + 1: {                                                                                            \
         float2 lg = __fmul2_rn(make_float2(lg2_approx(r[2 * (q)]), lg2_approx(r[2 * (q) + 1])),                \
@@ -733,101 +686,84 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
         lg.x = fmaxf(lg.x, floor_v);                                                                           \
         lg.y = fmaxf(lg.y, floor_v);                                                                           \
         lg = __ffma2_rn(lg, make_float2(0.25f, 0.25f), make_float2(1.0f, 1.0f)); /* (x+4)/4, TF-FE:161 */       \
-        if (va) *reinterpret_cast<float2*>(of + (q) * kNFrames) = lg;                                          \
+        if (va) of[(q) * kNFrames] = lg.x;                                                                     \
+        if (vb) of[(q) * kNFrames + 16] = lg.y;                                                                \
     }
-                        switch (nf) {   // fall-through: exactly nf rows, static register indices
-                            WLM_OUT_ROW(7) WLM_OUT_ROW(6) WLM_OUT_ROW(5) WLM_OUT_ROW(4)
-                            WLM_OUT_ROW(3) WLM_OUT_ROW(2) WLM_OUT_ROW(1) WLM_OUT_ROW(0)
-                            default: break;
-                        }
+                switch (nf) {   // fall-through: exactly nf rows, static register indices
+                    WLM_OUT_ROW(7) WLM_OUT_ROW(6) WLM_OUT_ROW(5) WLM_OUT_ROW(4)
+                    WLM_OUT_ROW(3) WLM_OUT_ROW(2) WLM_OUT_ROW(1) WLM_OUT_ROW(0)
+                    default: break;
+                }
 #undef WLM_OUT_ROW
-                    }
-                    // tiles of mine that hold no real sample: log-mel is exactly -10 everywhere
-                    for (int tile = rank + pend_n_my * kCluster; tile < kTilesPerClip; tile += kCluster) {
-                        float* of = ob + tile * kTile;
-                        if (tile * kTile + pair_frame_a(lane) < kNFrames)
-                            for (int q = 0; q < nf; ++q) *reinterpret_cast<float2*>(of + q * kNFrames) = make_float2(silent, silent);
-                    }
-                }
-                pend = false;
             }
-            // ---- B: mel stage of the previous tile ---------------------------------------------------------
-            const bool clip_ends = prev.valid && prev.last;
-            const bool mel_tile = prev.valid && prev.has_tile;
-            const int cpar = clip_ord & 1;
-            if (mel_tile) {
-                mbar_wait(bar_pfull, prev_tnum & 1);
-                float2 m2 = make_float2(0.f, 0.f);
-                for (int i = 0; i < n_runs; ++i) {
-                    const uint32_t tcol = tquart + static_cast<uint32_t>((win0 + i) * kTmemColsPerWarp + prev.j * kTmemColsPerTile);
-                    const float2 r2 = NMELS == 0 ? mel_stage(kt, P, run_of(i), lane, tcol)
-                                                 : mel_fixed<NMELS == 0 ? 80 : NMELS>(kt, P, run_of(i), lane, tcol);
-                    m2.x = fmaxf(m2.x, r2.x);
-                    m2.y = fmaxf(m2.y, r2.y);
+            // tiles of mine that hold no real sample: log-mel is exactly -10 everywhere
+            const float silent = (floor_v + 4.0f) * 0.25f;
+            for (int tile = rank + pend_n_my * kCluster; tile < kTilesPerClip; tile += kCluster) {
+                const int fa = tile * kTile + pair_frame_a(lane);
+                float* of = ob + tile * kTile;
+                for (int q = 0; q < nf; ++q) {
+                    if (fa < kNFrames) of[q * kNFrames] = silent;
+                    if (fa + 16 < kNFrames) of[q * kNFrames + 16] = silent;
                 }
-                if (prev.tile * kTile + pair_frame_a(lane) < kNFrames) {     // frames past 3000 do not exist
-                    mx.x = fmaxf(mx.x, m2.x);
-                    mx.y = fmaxf(mx.y, m2.y);
-                }
-                if (clip_ends) {
-                    float v = fmaxf(mx.x, mx.y);
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-                    if (lane == 0) warp_max[cpar * 8 + bw] = v;
-                    mx = make_float2(0.f, 0.f);
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_pfree);   // phase prev_tnum
             }
-            // ---- D: the clip ended: deliver the CTA's max to every CTA of the cluster (DSMEM) ---------------------
-            if (clip_ends) {
-                if (bw == 7) {   // the warp without stage-2 work
-                    if (mel_tile) mbar_wait(bar_pfree, prev_tnum & 1);   // every warp's warp_max is visible
-                    float c = (mel_tile && lane < kTeamWarps) ? warp_max[cpar * 8 + lane] : 0.f;
-#pragma unroll
-                    for (int o = 4; o > 0; o >>= 1) c = fmaxf(c, __shfl_xor_sync(0xffffffffu, c, o));
-                    c = __shfl_sync(0xffffffffu, c, 0);
-                    if (lane < kCluster) {
-                        // remote store into peer `lane`'s clip_max[cpar][rank], then arrive on its clip barrier
-                        uint32_t rslot, rbar;
-                        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rslot) : "r"(smem_u32(clip_max + cpar * 8 + rank)), "r"(lane));
-                        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(bar_clip0 + 8 * cpar), "r"(lane));
-                        asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(rslot), "f"(c) : "memory");
-                        asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(rbar) : "memory");
-                    }
-                }
-                pend = true;
-                pend_b = prev.cc.b;
-                pend_n_my = prev.n_my;
-                pend_ord = clip_ord;
-                ++clip_ord;
-            }
-            // ---- C: stage 2, both halves ---------------------------------------------------------------------
-            if (do_tile && s2) {
-#pragma unroll 1
-                for (int hh = 0; hh < 2; ++hh) {
-                    mbar_wait(bar_yfull0 + 8 * hh, tnum & 1);
-                    stage2(L, bw == 0, Y + hh * kYFloat2, P, hh, lane,
-                           [&]() {
-                               __syncwarp();
-                               if (lane == 0) mbar_arrive(bar_yfree0 + 8 * hh);   // phase tnum
-                           },
-                           [&]() {   // the mel stage of the previous tile must have read P (all 8 warps)
-                               if (hh == 0 && tnum > 0) mbar_wait(bar_pfree, (tnum - 1) & 1);
-                           });
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_pfull);   // phase tnum
-            }
-            prev = cur;
-            prev_tnum = tnum;
-            if (do_tile) ++tnum;
-            cur = cur.valid ? next_step(cur) : cur;
+            pend = false;
         }
+        // ---- B: mel stage of the previous tile -------------------------------------------------------------
+        const bool clip_ends = prev.valid && prev.last;
+        const bool mel_tile = prev.valid && prev.has_tile;
+        const int cpar = fin_parity;             // F has run: this is the parity of the clip ending now
+        if (mel_tile) {
+            mbar_wait(bar_pfull, prev_tnum & 1);
+            const uint32_t tcol = twin + prev.j * kTmemColsPerTile;
+            const float2 m2 = NMELS == 0 ? mel_stage(kt, P, warp, lane, tcol) : mel_fixed<NMELS == 0 ? 80 : NMELS>(kt, P, warp, lane, tcol);
+            const int fa = prev.tile * kTile + pair_frame_a(lane);     // frames past 3000 do not exist
+            if (fa < kNFrames) mx.x = fmaxf(mx.x, m2.x);
+            if (fa + 16 < kNFrames) mx.y = fmaxf(mx.y, m2.y);
+            if (clip_ends) {
+                float v = fmaxf(mx.x, mx.y);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+                if (lane == 0) warp_max[cpar * kWarps + warp] = v;
+                mx = make_float2(0.f, 0.f);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_pfree);   // phase prev_tnum
+        }
+        // ---- D: the clip ended: CTA max -> cta_max (every warp writes the same value), cluster ARRIVE ---------
+        // Done before stage 2 so that the peers get a whole step of slack before anyone WAITs (F, next step).
+        if (clip_ends) {
+            if (mel_tile) mbar_wait(bar_pfree, prev_tnum & 1);   // every warp's warp_max is visible
+            float c = (mel_tile && lane < kWarps) ? warp_max[cpar * kWarps + lane] : 0.f;
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) c = fmaxf(c, __shfl_xor_sync(0xffffffffu, c, o));
+            if (lane == 0) cta_max[cpar] = c;
+            asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+            pend = true;
+            pend_b = prev.cc.b;
+            pend_n_my = prev.n_my;
+        }
+        // ---- C: stage 2 ----------------------------------------------------------------------------------
+        if (do_tile && warp < fft::kNumSlots) {
+            mbar_wait(bar_yfull, tnum & 1);
+            stage2(kt, Y, P, warp, lane,
+                   [&]() {
+                       __syncwarp();
+                       if (lane == 0) mbar_arrive(bar_yfree);   // phase tnum
+                   },
+                   [&]() {   // the mel stage of the previous tile must have read P (all 16 warps)
+                       if (tnum > 0) mbar_wait(bar_pfree, (tnum - 1) & 1);
+                   });
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_pfull);   // phase tnum
+        }
+        prev = cur;
+        prev_tnum = tnum;
+        if (do_tile) ++tnum;
+        cur = cur.valid ? next_step(cur) : cur;
     }
     // all TMEM reads are complete (tcgen05.wait::ld inside tmem_ld_x16); release the allocation
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    cluster.sync();   // no CTA leaves while a peer may still write its clip_max / arrive on its barriers
+    cluster.sync();   // also keeps every CTA's shared memory alive until its peers have read cta_max
     if (warp == 0) tmem_dealloc_512(tmem_base);
 }
 
