@@ -323,19 +323,20 @@ __device__ __forceinline__ void tile_fixup(const ClipArgs& a, const ClipCtx& c, 
 }
 
 // ---- stage 1 ----------------------------------------------------------------------------------
-// warp w, lane (n1 = lane & 15, g = lane >> 4): frames (32 g + w, 32 g + w + 16) of the tile.
+// warp w, lane (n1 = lane & 15, g = lane >> 4): the two ADJACENT frames 32 g + 2 w, 32 g + 2 w + 1 of the tile
+// (pair index 16 g + w = lane of the later stages, whose outputs are then one float2 per lane).
 // `loaded()` runs once the warp no longer needs the raw buffer, `before_store()` just before Y is written.
 template <class Loaded, class BeforeStore>
 __device__ __forceinline__ void stage1(const float* raw, float2* Y, const float (&wv)[25], int tw, int warp, int lane,
                                        Loaded loaded, BeforeStore before_store) {
     const int n1 = lane & 15, g = lane >> 4;
-    const float* p0 = raw + g * kRegion + kHop * warp + 25 * n1;
+    const float* p0 = raw + g * kRegion + 2 * kHop * warp + 25 * n1;
     const float* p1 = p0 - kNfft;
     V2 y[25];
 #pragma unroll
     for (int t = 0; t < 25; ++t) {
         const float* p = (t >= tw) ? p1 : p0;
-        const float xa = p[16 * t], xb = p[16 * t + 16 * kHop];
+        const float xa = p[16 * t], xb = p[16 * t + kHop];
         y[t] = mk(xa * wv[t], xb * wv[t]);
     }
     loaded();      // (fence inside: every LDS above has been performed)
@@ -380,8 +381,8 @@ __device__ __forceinline__ void stage2(const KernelTables& kt, const float2* Y, 
     }
 }
 
-// lane = frame pair: frames (lane, lane+16) for lane < 16, (lane+16, lane+32) for lane >= 16
-__device__ __forceinline__ int pair_frame_a(int lane) { return lane < 16 ? lane : lane + 16; }
+// lane = frame pair of the tile: frames (2 lane, 2 lane + 1)
+__device__ __forceinline__ int pair_frame_a(int lane) { return 2 * lane; }
 
 // ---- mel stage ------------------------------------------------------------------------------------
 // One warp, its run of <= 8 filters, 32 frame pairs.  Groups of bins between adjacent filter centres
@@ -629,11 +630,13 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
 
     while (cur.valid || prev.valid || pend) {
         const bool do_tile = cur.valid && cur.has_tile;
+        const Step nxt = cur.valid ? next_step(cur) : cur;
+        Step nt = nxt;                                   // next step that owns a tile: target of the TMA re-arm
+        while (nt.valid && !nt.has_tile) nt = next_step(nt);
         // ---- A: stage 1 ----------------------------------------------------------------------------
         if (do_tile) {
             mbar_wait(bar_raw, tnum & 1);
             tile_fixup(a, cur.cc, cur.tile, raw);
-            const Step nt = next_tile_step(cur);
             stage1(raw, Y, wv, tw, warp, lane,
                    [&]() {   // this warp is done with raw: the last of the 16 re-arms the TMA for the next tile
                        __syncwarp();
@@ -678,7 +681,7 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
                 const int f0 = (rank + j * kCluster) * kTile;
                 const int fa = f0 + pair_frame_a(lane);
                 float* of = ob + f0;
-                const bool va = fa < kNFrames, vb = fa + 16 < kNFrames;
+                const bool va = fa < kNFrames;      // 3000 is even: both frames of the pair or none
 #define WLM_OUT_ROW(q)                                                                                         \
     case (q) + 1: {                                                                                            \
         float2 lg = __fmul2_rn(make_float2(lg2_approx(r[2 * (q)]), lg2_approx(r[2 * (q) + 1])),                \
@@ -686,8 +689,7 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
         lg.x = fmaxf(lg.x, floor_v);                                                                           \
         lg.y = fmaxf(lg.y, floor_v);                                                                           \
         lg = __ffma2_rn(lg, make_float2(0.25f, 0.25f), make_float2(1.0f, 1.0f)); /* (x+4)/4, TF-FE:161 */       \
-        if (va) of[(q) * kNFrames] = lg.x;                                                                     \
-        if (vb) of[(q) * kNFrames + 16] = lg.y;                                                                \
+        if (va) *reinterpret_cast<float2*>(of + (q) * kNFrames) = lg;                                          \
     }
                 switch (nf) {   // fall-through: exactly nf rows, static register indices
                     WLM_OUT_ROW(7) WLM_OUT_ROW(6) WLM_OUT_ROW(5) WLM_OUT_ROW(4)
@@ -701,10 +703,8 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
             for (int tile = rank + pend_n_my * kCluster; tile < kTilesPerClip; tile += kCluster) {
                 const int fa = tile * kTile + pair_frame_a(lane);
                 float* of = ob + tile * kTile;
-                for (int q = 0; q < nf; ++q) {
-                    if (fa < kNFrames) of[q * kNFrames] = silent;
-                    if (fa + 16 < kNFrames) of[q * kNFrames + 16] = silent;
-                }
+                if (fa < kNFrames)
+                    for (int q = 0; q < nf; ++q) *reinterpret_cast<float2*>(of + q * kNFrames) = make_float2(silent, silent);
             }
             pend = false;
         }
@@ -716,9 +716,10 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
             mbar_wait(bar_pfull, prev_tnum & 1);
             const uint32_t tcol = twin + prev.j * kTmemColsPerTile;
             const float2 m2 = NMELS == 0 ? mel_stage(kt, P, warp, lane, tcol) : mel_fixed<NMELS == 0 ? 80 : NMELS>(kt, P, warp, lane, tcol);
-            const int fa = prev.tile * kTile + pair_frame_a(lane);     // frames past 3000 do not exist
-            if (fa < kNFrames) mx.x = fmaxf(mx.x, m2.x);
-            if (fa + 16 < kNFrames) mx.y = fmaxf(mx.y, m2.y);
+            if (prev.tile * kTile + pair_frame_a(lane) < kNFrames) {     // frames past 3000 do not exist
+                mx.x = fmaxf(mx.x, m2.x);
+                mx.y = fmaxf(mx.y, m2.y);
+            }
             if (clip_ends) {
                 float v = fmaxf(mx.x, mx.y);
 #pragma unroll
@@ -759,7 +760,7 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
         prev = cur;
         prev_tnum = tnum;
         if (do_tile) ++tnum;
-        cur = cur.valid ? next_step(cur) : cur;
+        cur = nxt;
     }
     // all TMEM reads are complete (tcgen05.wait::ld inside tmem_ld_x16); release the allocation
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
