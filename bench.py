@@ -171,8 +171,14 @@ def run_ours(args, wl, rank, world, local_rank):
         dist = dist_mod
         dist.init_process_group(backend="nccl", device_id=dev)
 
+    from whisper_context_biasing_b200.sharding import clip_shard
+
     n_mels = wl["n_mels"]
-    B = wl["batch"] // world if wl["strong"] else wl["batch"]
+    if wl["strong"]:                       # one global batch, contiguous clips per rank
+        lo, hi = clip_shard(wl["batch"], rank, world)
+        B = hi - lo
+    else:                                  # the same batch size on every rank
+        B = wl["batch"]
     fe = W.B200WhisperFeatureExtractor(feature_size=n_mels, device=dev)
 
     # synthetic PCM (family F1, white Gaussian sigma 0.1), generated on the host, pinned
@@ -244,7 +250,7 @@ def run_ours(args, wl, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_ms, e2e_ms, launch_ms, e2e_wall_ms = [float(v) for v in t.tolist()]
 
-    total_clips = B * world
+    total_clips = wl["batch"] if wl["strong"] else B * world
     value = CLIP_SECONDS * total_clips * args.steps / (dev_ms * 1e-3)
     e2e_value = CLIP_SECONDS * total_clips * e2e_steps / (e2e_ms * 1e-3)
     peak, peak_src = measured_peaks()

@@ -92,6 +92,11 @@ int wlm_plan_destroy(wlm_plan* plan);
 int wlm_plan_n_mels(const wlm_plan* plan);
 int wlm_plan_device(const wlm_plan* plan);
 int wlm_plan_sm_count(const wlm_plan* plan);
+/* 80 / 128: the mel stage runs unrolled with the structure of that Whisper bank baked in (the
+ * caller's table has exactly that structure); 0: table-driven mel stage (any other valid table). */
+int wlm_plan_kernel_variant(const wlm_plan* plan);
+/* Thread-block clusters of the fused kernel that are co-resident on the device (persistent grid). */
+int wlm_plan_max_clusters(const wlm_plan* plan);
 
 /*
  * Device scratch needed by wlm_logmel for a batch of B clips (bytes, 256-aligned).

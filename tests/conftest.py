@@ -27,10 +27,12 @@ def golden():
 def _built_library():
     """libwlm.so is git-ignored: build it in-tree when missing/stale and nvcc is present (the
     build container); on the GPU box the prebuilt file travels with the snapshot."""
+    import importlib.util
     import shutil
 
-    from whisper_context_biasing_b200 import build as B
-
+    spec = importlib.util.spec_from_file_location("_wlm_build", os.path.join(ROOT, "whisper_context_biasing_b200", "build.py"))
+    B = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(B)          # by path: importing the package would dlopen a stale library first
     if B.needs_build() and (shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc")):
         B.build_library()
     yield

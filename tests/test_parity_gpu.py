@@ -41,6 +41,37 @@ def test_native_library_is_loaded(fe):
     assert fe[80].launch_count == 0
 
 
+def test_kernel_variants(fe):
+    """80 / 128 mels run the unrolled mel stage; any other bank the table-driven one, same parity."""
+    from whisper_context_biasing_b200 import B200WhisperFeatureExtractor
+
+    assert fe[80].kernel_variant == 80 and fe[128].kernel_variant == 128
+    assert fe[80].max_clusters >= 1
+    clips = [O.synth_clip("speech", 480000, 21), O.synth_clip("chirp", 100000, 22), O.synth_clip("gap", 300000, 23)]
+    for m in (40, 64, 100):
+        ex = B200WhisperFeatureExtractor(feature_size=m)
+        assert ex.kernel_variant == 0
+        got = ex(clips, sampling_rate=16000, return_tensors="np").input_features
+        ref = O.extract(clips, m, "f64")
+        assert got.shape == (3, m, 3000)
+        assert np.abs(got - ref).max() <= TOL, (m, np.abs(got - ref).max())
+        ex.close()
+
+
+def test_pageable_and_pinned_host_sources_agree(fe):
+    import torch
+
+    ex = fe[80]
+    clips = [O.synth_clip("noise", L, 30 + i) for i, L in enumerate([480000, 77777, 480000, 1234])]
+    a = ex.extract_host(clips).cpu().numpy()                       # pageable numpy -> pinned ring
+    pinned = [torch.from_numpy(c).pin_memory() for c in clips]
+    b = ex.extract_host([p.numpy() for p in pinned]).cpu().numpy()   # pinned -> direct async copies
+    assert np.array_equal(a, b)
+    out_host = np.empty((4, 80, 3000), np.float32)
+    c = ex.extract_host(clips, out_host=out_host).cpu().numpy()    # D2H inside the call
+    assert np.array_equal(a, c) and np.array_equal(a, out_host)
+
+
 def test_golden_vectors(fe, golden):
     z, meta = golden
     fs = np.array(meta["frame_subsample"])

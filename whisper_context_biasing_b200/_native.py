@@ -29,6 +29,8 @@ SYMBOLS = {
     "wlm_plan_n_mels": (_i, [_vp]),
     "wlm_plan_device": (_i, [_vp]),
     "wlm_plan_sm_count": (_i, [_vp]),
+    "wlm_plan_kernel_variant": (_i, [_vp]),
+    "wlm_plan_max_clusters": (_i, [_vp]),
     "wlm_workspace_bytes": (_sz, [_vp, _i]),
     "wlm_logmel": (_i, [_vp, _vp, _i, _vp, _vp, _i64, _i, _vp, _vp, _vp, _sz, _vp]),
     "wlm_frame_mask": (_i, [_vp, _vp, _i, _vp, _vp]),

@@ -157,6 +157,15 @@ class B200WhisperFeatureExtractor:
     def launch_count(self) -> int:
         return int(N.LIB.wlm_plan_launch_count(self._plan))
 
+    @property
+    def kernel_variant(self) -> int:
+        """80 / 128: unrolled mel stage for that Whisper bank; 0: table-driven mel stage."""
+        return int(N.LIB.wlm_plan_kernel_variant(self._plan))
+
+    @property
+    def max_clusters(self) -> int:
+        return int(N.LIB.wlm_plan_max_clusters(self._plan))
+
     # -- helpers -----------------------------------------------------------------------------
     def _stream(self):
         import torch
