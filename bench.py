@@ -60,7 +60,7 @@ class ClockSampler(threading.Thread):
                0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
                0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
 
-    def __init__(self, index: int, period_s: float = 0.02):
+    def __init__(self, index: int, period_s: float = 0.002):
         super().__init__(daemon=True)
         self.index, self.period = index, period_s
         self.samples, self.reasons, self.max_mhz = [], set(), None
@@ -128,7 +128,7 @@ def run_reference(args, wl, rank, world):
 
     cores = len(os.sched_getaffinity(0))
     # bounded sample: ~cores * 12 clips per step keeps a step to a few seconds of host time
-    clips_per_step = max(16, min(wl["batch"], cores * 12))
+    clips_per_step = max(16, min(wl["batch"], cores * 16))
     clips_per_step = (clips_per_step + 15) // 16 * 16
     clips = synth_noise_clips(min(clips_per_step, 64), seed=1)
     clips = [clips[i % len(clips)] for i in range(clips_per_step)]
@@ -275,7 +275,7 @@ def run_ours(args, wl, rank, world, local_rank):
                             "features stay in HBM; D2H of one float per clip"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": KERNEL_DRAM_TRAFFIC_BYTES.get(n_mels),
+                         "frac": achieved / peak, "traffic": (int(KERNEL_DRAM_TRAFFIC_PER_CLIP[n_mels] * B) if n_mels in KERNEL_DRAM_TRAFFIC_PER_CLIP else None),
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                          "launch_ms": launch_ms},
             "clocks": clocks,
@@ -288,10 +288,11 @@ def run_ours(args, wl, rank, world, local_rank):
         dist.destroy_process_group()
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel for one launch of the
-# default workload, from the `ncu --set full` capture summarised under profiles/ (None = not
-# captured yet for this kernel version).
-KERNEL_DRAM_TRAFFIC_BYTES = {80: 700240384, 128: None}   # profiles/r01_step7_cluster6_summary.txt: 491.59 + 208.66 MB
+# dram__bytes_read.sum + dram__bytes_write.sum of the fused kernel per clip, from the `ncu --set full`
+# captures summarised under profiles/ (r01_c2_80mel_summary.txt: 491.59 + 208.66 MB for 256 clips;
+# r01_c3_128mel_summary.txt: 1966.18 + 1522.33 MB for 1024 clips).  Algorithmic: 2.88 / 3.456 MB per clip;
+# the measured traffic is slightly lower because the tail of the output is still dirty in L2 at kernel end.
+KERNEL_DRAM_TRAFFIC_PER_CLIP = {80: 700240384 / 256, 128: 3488505000 / 1024}
 
 
 def cpu_baseline(n_mels):
@@ -299,7 +300,7 @@ def cpu_baseline(n_mels):
     from oracle.hf_reference import time_reference_dataloader
 
     cores = len(os.sched_getaffinity(0))
-    n = max(32, min(cores * 16, 512))
+    n = max(64, min(cores * 64, 2048))           # ~10-30 s of single-core work
     n = (n + 15) // 16 * 16
     base = synth_noise_clips(min(n, 32), seed=1)
     clips = [base[i % len(base)] for i in range(n)]
