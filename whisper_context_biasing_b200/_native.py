@@ -8,7 +8,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libwlm.so")
+_LIB_PATH = os.environ.get("WLM_LIBRARY_PATH") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libwlm.so")
 
 WLM_OK = 0
 WLM_ERR_BAD_ARG = -1

@@ -183,7 +183,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "{\n"
         ".reg .pred p;\n"
         "WAIT_%=:\n"
+#ifdef WLM_OPT_HINT
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n"   /* suspend-time hint: sleep, do not spin */
+#else
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+#endif
         "@p bra DONE_%=;\n"
         "bra WAIT_%=;\n"
         "DONE_%=:\n"
@@ -630,9 +634,15 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
 
     while (cur.valid || prev.valid || pend) {
         const bool do_tile = cur.valid && cur.has_tile;
-        const Step nxt = cur.valid ? next_step(cur) : cur;
-        Step nt = nxt;                                   // next step that owns a tile: target of the TMA re-arm
-        while (nt.valid && !nt.has_tile) nt = next_step(nt);
+        Step nxt = cur, nt = cur;                        // next step / next step that owns a tile (TMA re-arm target)
+        if (cur.valid) {
+            bool first = true;
+#pragma unroll 1
+            do {
+                nt = next_step(nt);
+                if (first) { nxt = nt; first = false; }
+            } while (nt.valid && !nt.has_tile);
+        }
         // ---- A: stage 1 ----------------------------------------------------------------------------
         if (do_tile) {
             mbar_wait(bar_raw, tnum & 1);
@@ -744,9 +754,16 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
             pend_n_my = prev.n_my;
         }
         // ---- C: stage 2 ----------------------------------------------------------------------------------
-        if (do_tile && warp < fft::kNumSlots) {
+        // 13 slots on 16 warps: one scheduler gets 4 tasks, the others 3.  Rotating the assignment by one
+        // warp per tile moves the extra task around, so over four tiles every scheduler issues the same work.
+#ifdef WLM_OPT_ROT
+        const int slot = (warp + tnum) & 15;
+#else
+        const int slot = warp;
+#endif
+        if (do_tile && slot < fft::kNumSlots) {
             mbar_wait(bar_yfull, tnum & 1);
-            stage2(kt, Y, P, warp, lane,
+            stage2(kt, Y, P, slot, lane,
                    [&]() {
                        __syncwarp();
                        if (lane == 0) mbar_arrive(bar_yfree);   // phase tnum
