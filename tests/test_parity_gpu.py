@@ -264,3 +264,49 @@ def test_encoder_output_cosine(fe):
     pos = torch.nn.functional.cosine_similarity(a, b, dim=2).min()
     print("encoder cosine per clip", cos.tolist(), "min per-position", float(pos))
     assert float(cos.min()) >= 0.9999
+
+
+def test_collator_step_c5(fe):
+    """BASELINE configs[4]: full collator step -- PCM items + prompt/label tokens + bias spans -> batch dict
+    with device-resident features -> random-init whisper-small encoder, parity with the reference features.
+    Clip lengths follow the C4 rule d = clip(0.4 + words / 2.6, 1, 30) s."""
+    import torch
+
+    tr = pytest.importorskip("transformers")
+    from oracle.hf_reference import hf_features
+    from whisper_context_biasing_b200 import B200DataCollatorSpeechSeq2SeqWithPadding
+
+    ex = fe[80]
+    rng = np.random.default_rng(4)
+    words = rng.integers(1, 26, 16)
+    secs = np.clip(0.4 + words / 2.6, 1.0, 30.0)
+    SOT, PREV, PAD = 257, 360, 256
+    items = []
+    for i, d in enumerate(secs):
+        pcm = O.synth_clip("speech", int(d * 16000), 400 + i)
+        prompt = [PREV] + rng.integers(0, 256, int(rng.integers(3, 30))).tolist()
+        labels = prompt + [SOT] + rng.integers(0, 256, int(words[i]) * 5).tolist() + [PAD]
+        spans = [rng.integers(0, 256, int(rng.integers(1, 8))).tolist() for _ in range(int(rng.integers(0, 4)))]
+        items.append({"audio": pcm, "labels": labels, "bias_spans": spans})
+    coll = B200DataCollatorSpeechSeq2SeqWithPadding(feature_extractor=ex, pad_token_id=PAD, decoder_start_token_id=SOT,
+                                                    decoder_prev_token_id=PREV)
+    batch = coll(items)
+    feats = batch["input_features"]
+    assert feats.is_cuda and tuple(feats.shape) == (16, 80, 3000)
+    assert batch["labels"].shape == batch["decoder_input_ids"].shape and batch["bias_spans"].dim() == 3
+    assert (batch["labels"][:, 0] == -100).all()                   # prompt masked up to <|startoftranscript|>
+    ref = torch.from_numpy(hf_features([it["audio"] for it in items], 80, "default")).to(ex.device)
+    assert float((ref - feats).abs().max()) <= TOL_CONTRACT
+    torch.manual_seed(0)
+    cfg = tr.WhisperConfig(d_model=768, encoder_layers=12, encoder_attention_heads=12, encoder_ffn_dim=3072,
+                           decoder_layers=1, decoder_attention_heads=12, decoder_ffn_dim=3072, num_mel_bins=80)
+    enc = tr.WhisperModel(cfg).get_encoder().to(ex.device).eval()
+    with torch.no_grad():
+        a = enc(ref[:4]).last_hidden_state.float()
+        b = enc(feats[:4]).last_hidden_state.float()
+    cos = torch.nn.functional.cosine_similarity(a.flatten(1), b.flatten(1), dim=1)
+    assert float(cos.min()) >= 0.9999
+    # items that already carry features are stacked like the reference collator does
+    pre = [{"input_features": feats[i], "labels": items[i]["labels"], "bias_spans": items[i]["bias_spans"]} for i in range(3)]
+    b2 = coll(pre)
+    assert torch.equal(b2["input_features"], feats[:3])
