@@ -187,6 +187,9 @@ def run_ours(args, wl, rank, world, local_rank):
         import torch.distributed as dist_mod
 
         dist = dist_mod
+        # NCCL prints "NCCL version ..." to stdout at VERSION level; keep stdout to the one JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group(backend="nccl", device_id=dev)
 
     from whisper_context_biasing_b200.sharding import clip_shard
