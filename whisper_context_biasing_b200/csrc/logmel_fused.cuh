@@ -89,8 +89,8 @@ struct KernelTables {
     int16_t m0[kWarps];                             // first filter of warp w
     int16_t nf[kWarps];                             // number of filters of warp w (<= 8)
     // stage 2: per k2 slot, float2 offsets into Y (component) and into P (output bin) per FFT16 output
-    int16_t slot_comp_off[16];                      // comp * 32
-    int16_t slot_pbin_off[13][16];                  // output_bin(k1, k2) * 32, indexed by cfft16 array position
+    int32_t slot_comp_off[16];                      // comp * 32
+    int32_t slot_pbin_off[13][16];                  // BYTE offset of output_bin(k1, k2) in P, indexed by cfft16 array position
     int16_t n_mels;
 };
 using MelParams = KernelTables;
@@ -163,9 +163,9 @@ inline int build_tables(const MelSparse& sp, int n_mels, Tables* t, int* variant
     }
     if (m < n_mels) return -1;
     for (int s2 = 0; s2 < fft::kNumSlots; ++s2) {
-        mp.slot_comp_off[s2] = (int16_t)(fft::kSlotComp[s2] * 32);
+        mp.slot_comp_off[s2] = fft::kSlotComp[s2] * 32;
         for (int k1 = 0; k1 < 16; ++k1)
-            mp.slot_pbin_off[s2][fft::fft16_slot_of_k1(k1)] = (int16_t)(fft::output_bin(k1, fft::kSlotK2[s2]) * 32);
+            mp.slot_pbin_off[s2][fft::fft16_slot_of_k1(k1)] = fft::output_bin(k1, fft::kSlotK2[s2]) * 32 * 8;
     }
     return 0;
 }
@@ -363,25 +363,23 @@ __device__ __forceinline__ void stage2(const KernelTables& kt, const float2* Y, 
     const float2* yl = Y + kt.slot_comp_off[slot] + lane;
     V2 xr[16], xi[16];
 #pragma unroll
-    for (int n1 = 0; n1 < 16; ++n1) xr[n1].v = yl[n1 * kYStride];
-    if (slot != 0) {
-#pragma unroll
-        for (int n1 = 0; n1 < 16; ++n1) xi[n1].v = yl[n1 * kYStride + 32];
-    } else {  // k2 = 0: Y is purely real
+    for (int n1 = 0; n1 < 16; ++n1) {
+        xr[n1].v = yl[n1 * kYStride];
+        xi[n1].v = yl[n1 * kYStride + 32];      // slot 0 (k2 = 0, purely real Y): fetches component 1, discarded below
+    }
+    loaded();
+    if (slot == 0) {
 #pragma unroll
         for (int n1 = 0; n1 < 16; ++n1) xi[n1] = mk(0.f, 0.f);
     }
     fft::cfft16<V2>(xr, xi);
-    V2 pw[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) pw[i] = vfma(xr[i], xr[i], vmul(xi[i], xi[i]));
-    loaded();
     before_store();
-    float2* pl = P + lane;
+    char* pl = reinterpret_cast<char*>(P + lane);
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
         // slot 0 writes bins 25 j twice (k1 and 16-k1 are conjugates): same thread, same value class
-        pl[kt.slot_pbin_off[slot][i]] = pw[i].v;
+        const V2 pw = vfma(xr[i], xr[i], vmul(xi[i], xi[i]));
+        *reinterpret_cast<float2*>(pl + kt.slot_pbin_off[slot][i]) = pw.v;
     }
 }
 
@@ -576,42 +574,33 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
     //   B  mel stage of t_{i-1}      wait P full | ... | arrive P free
     //   D  if t_{i-1} ended a clip:  wait P free | CTA max -> cta_max | cluster barrier ARRIVE
     //   C  stage 2 of t_i (13 warps) wait Y full | load | arrive Y free | FFT | wait P free | store | arrive P full
-    struct Step {
-        bool valid, has_tile, last;
-        int j, n_my, tile;
-        ClipCtx cc;
-    };
-    auto first_step_of_clip = [&](int bb) {
-        Step s;
-        s.valid = bb < a.B;
-        s.j = 0;
-        s.tile = rank;
-        s.n_my = 0;
-        s.has_tile = false;
-        s.last = true;
-        if (s.valid) {
-            s.cc = clip_ctx(a, bb);
-            s.n_my = s.cc.n_act > rank ? (s.cc.n_act - rank + kCluster - 1) / kCluster : 0;
-            s.has_tile = s.n_my > 0;
-            s.last = s.n_my <= 1;
-        } else {
-            s.cc.b = bb; s.cc.len = 0; s.cc.n_act = 0; s.cc.base = 0;
+    // Iteration state kept in plain scalars (a struct-per-step version spent ~100 instructions per warp and
+    // step on copies): `c*` = the step whose tile is in stage 1 / stage 2, `p*` = the previous step (mel stage).
+    auto my_tiles = [&](int n_act) { return n_act > rank ? (n_act - rank + kCluster - 1) / kCluster : 0; };
+    int cb = cluster_id, cj = 0, cn_my = 0;          // clip, step inside the clip, tiles of mine in the clip
+    bool cvalid = cb < a.B;
+    ClipCtx cc;
+    cc.b = cb; cc.len = 0; cc.n_act = 0; cc.base = 0;
+    if (cvalid) {
+        cc = clip_ctx(a, cb);
+        cn_my = my_tiles(cc.n_act);
+    }
+    bool pvalid = false, phas = false, plast = false;
+    int pb = 0, pj = 0, ptile = 0, pn_my = 0;
+    // TMA target after tile (clip cb0, step j0): the next tile of the same clip, else the first tile of the
+    // next clip in which this CTA owns one.  Executed by ONE lane (the last warp to finish reading raw).
+    auto issue_next_tile = [&](int cb0, const ClipCtx& c0, int n_my0, int j0) {
+        if (j0 + 1 < n_my0) {
+            tile_issue_tma(a, c0, rank + (j0 + 1) * kCluster, raw, bar_raw);
+            return;
         }
-        return s;
-    };
-    auto next_step = [&](const Step& c) {
-        if (!c.last) {
-            Step s = c;
-            s.j = c.j + 1;
-            s.tile = c.tile + kCluster;
-            s.last = s.j == c.n_my - 1;
-            return s;
+        for (int nb = cb0 + n_clusters; nb < a.B; nb += n_clusters) {
+            const ClipCtx c2 = clip_ctx(a, nb);
+            if (c2.n_act > rank) {
+                tile_issue_tma(a, c2, rank, raw, bar_raw);
+                return;
+            }
         }
-        return first_step_of_clip(c.cc.b + n_clusters);
-    };
-    auto next_tile_step = [&](Step s) {      // first step after `s` that owns a tile (or invalid)
-        do { s = next_step(s); } while (s.valid && !s.has_tile);
-        return s;
     };
 
     // Phase bookkeeping: the n-th tile this CTA processes (n = 0, 1, ...) uses phase n of every barrier,
@@ -619,34 +608,22 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
     // or whose own later work is needed to complete phase n+1, so the barrier is never more than one
     // phase ahead of a waiter.
     int fin_parity = 0;                      // parity of the clip whose max is exchanged next
-    Step cur = first_step_of_clip(cluster_id);
-    Step prev = cur;
-    prev.valid = false;
     int tnum = 0, prev_tnum = 0;             // ordinal of cur's / prev's tile among the tiles of this CTA
-    if (tid == 0) {
-        Step f = cur;
-        if (f.valid && !f.has_tile) f = next_tile_step(f);
-        if (f.valid) tile_issue_tma(a, f.cc, f.tile, raw, bar_raw);
+    if (tid == 0 && cvalid) {
+        if (cn_my > 0) tile_issue_tma(a, cc, rank, raw, bar_raw);
+        else issue_next_tile(cb, cc, 0, 0);
     }
     float2 mx = make_float2(0.f, 0.f);       // running max of the mel power of the clip in flight (>= 0)
     bool pend = false;                       // an output pass is owed (cluster barrier arrived, not yet waited)
     int pend_b = 0, pend_n_my = 0;
 
-    while (cur.valid || prev.valid || pend) {
-        const bool do_tile = cur.valid && cur.has_tile;
-        Step nxt = cur, nt = cur;                        // next step / next step that owns a tile (TMA re-arm target)
-        if (cur.valid) {
-            bool first = true;
-#pragma unroll 1
-            do {
-                nt = next_step(nt);
-                if (first) { nxt = nt; first = false; }
-            } while (nt.valid && !nt.has_tile);
-        }
+    while (cvalid || pvalid || pend) {
+        const bool do_tile = cvalid && cj < cn_my;
+        const int ctile = rank + cj * kCluster;
         // ---- A: stage 1 ----------------------------------------------------------------------------
         if (do_tile) {
             mbar_wait(bar_raw, tnum & 1);
-            tile_fixup(a, cur.cc, cur.tile, raw);
+            tile_fixup(a, cc, ctile, raw);
             stage1(raw, Y, wv, tw, warp, lane,
                    [&]() {   // this warp is done with raw: the last of the 16 re-arms the TMA for the next tile
                        __syncwarp();
@@ -657,7 +634,7 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
                                *raw_readers = 0;
                                __threadfence_block();
                                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                               if (nt.valid) tile_issue_tma(a, nt.cc, nt.tile, raw, bar_raw);
+                               issue_next_tile(cb, cc, cn_my, cj);
                            }
                        }
                    },
@@ -719,14 +696,14 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
             pend = false;
         }
         // ---- B: mel stage of the previous tile -------------------------------------------------------------
-        const bool clip_ends = prev.valid && prev.last;
-        const bool mel_tile = prev.valid && prev.has_tile;
+        const bool clip_ends = pvalid && plast;
+        const bool mel_tile = pvalid && phas;
         const int cpar = fin_parity;             // F has run: this is the parity of the clip ending now
         if (mel_tile) {
             mbar_wait(bar_pfull, prev_tnum & 1);
-            const uint32_t tcol = twin + prev.j * kTmemColsPerTile;
+            const uint32_t tcol = twin + pj * kTmemColsPerTile;
             const float2 m2 = NMELS == 0 ? mel_stage(kt, P, warp, lane, tcol) : mel_fixed<NMELS == 0 ? 80 : NMELS>(kt, P, warp, lane, tcol);
-            if (prev.tile * kTile + pair_frame_a(lane) < kNFrames) {     // frames past 3000 do not exist
+            if (ptile * kTile + pair_frame_a(lane) < kNFrames) {     // frames past 3000 do not exist
                 mx.x = fmaxf(mx.x, m2.x);
                 mx.y = fmaxf(mx.y, m2.y);
             }
@@ -750,8 +727,8 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
             if (lane == 0) cta_max[cpar] = c;
             asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
             pend = true;
-            pend_b = prev.cc.b;
-            pend_n_my = prev.n_my;
+            pend_b = pb;
+            pend_n_my = pn_my;
         }
         // ---- C: stage 2 ----------------------------------------------------------------------------------
         // 13 slots on 16 warps: one scheduler gets 4 tasks, the others 3.  Rotating the assignment by one
@@ -774,10 +751,26 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_pfull);   // phase tnum
         }
-        prev = cur;
+        // this step becomes the previous one; advance to the next step of the stream
+        const int steps = cn_my > 0 ? cn_my : 1;
+        pvalid = cvalid; phas = do_tile; plast = cvalid && cj + 1 >= steps;
+        pb = cb; pj = cj; ptile = ctile; pn_my = cn_my;
         prev_tnum = tnum;
         if (do_tile) ++tnum;
-        cur = nxt;
+        if (cvalid) {
+            if (cj + 1 < steps) {
+                ++cj;
+            } else {
+                cb += n_clusters;
+                cj = 0;
+                cn_my = 0;
+                cvalid = cb < a.B;
+                if (cvalid) {
+                    cc = clip_ctx(a, cb);
+                    cn_my = my_tiles(cc.n_act);
+                }
+            }
+        }
     }
     // all TMEM reads are complete (tcgen05.wait::ld inside tmem_ld_x16); release the allocation
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
