@@ -170,8 +170,34 @@ WLM_HD void cfft16(V (&xr)[16], V (&xi)[16]) {
 // after cfft16 the value for k1 = c + 4d sits at array index 4c + d:
 WLM_HD constexpr int fft16_slot_of_k1(int k1) { return 4 * (k1 & 3) + (k1 >> 2); }
 
-// same for a purely real input (slot 0, k2 = 0): only k1 = 0..8 are needed; imaginary inputs are
-// exact zeros, so the compiler folds roughly half of the arithmetic away.
+WLM_HD constexpr int fft16_k1_of_pos(int i) { return (i >> 2) + 4 * (i & 3); }
+
+// Stage 2 leaves |X|^2 of slot s, array position i, in row 16 s + i of its output buffer; the mel stage
+// walks FFT bins in order, so it needs the inverse: the row that holds bin k (slot 0 holds each of its
+// bins twice, k1 and 16 - k1 being conjugates: the first one is taken).
+struct RowOfBin {
+    short r[208];
+};
+WLM_HD constexpr RowOfBin make_row_of_bin() {
+    RowOfBin t{};
+    for (int k = 0; k < 208; ++k) t.r[k] = -1;
+    for (int s = 0; s < kNumSlots; ++s)
+        for (int i = 0; i < 16; ++i) {
+            const int k = output_bin(fft16_k1_of_pos(i), kSlotK2[s]);
+            if (t.r[k] < 0) t.r[k] = static_cast<short>(16 * s + i);
+        }
+    return t;
+}
+#ifdef __CUDACC__
+__device__ constexpr RowOfBin kRowOfBin = make_row_of_bin();
+#endif
+WLM_HD int row_of_bin(int k) {
+#ifdef __CUDA_ARCH__
+    return kRowOfBin.r[k];
+#else
+    return make_row_of_bin().r[k];
+#endif
+}
 
 }  // namespace fft
 }  // namespace wlm

@@ -1,22 +1,27 @@
 // Fused log-mel kernel for sm_100a.
 //
-// A thread-block CLUSTER of 6 CTAs owns one clip (3000 frames = 47 tiles of 64 frames, tile t goes to
-// CTA t mod 6).  Each CTA (16 warps) walks its tiles through
+// A thread-block CLUSTER of 6 CTAs owns one clip.  Every CTA runs TWO independent warp groups of 8
+// warps ("virtual CTAs"); the clip's 3000 frames are 94 half-tiles of 32 frames and half-tile u goes
+// to virtual CTA u mod 12 (= 2 * cluster rank + group).  A group walks its half-tiles through
 //
-//   TMA (cp.async.bulk, mbarrier)  raw PCM  ->  shared memory, two regions 16 banks apart
-//   stage 1  per warp: 4 frames x 16 sub-transforms; lane = (n1, frame group); 25-point real DFT of
+//   TMA (cp.async.bulk, mbarrier)  raw PCM  ->  shared memory, two sub-regions 16 banks apart
+//   stage 1  per warp: 4 frames x 16 sub-transforms; lane = (n1, sub-region); 25-point real DFT of
 //            the Hann-windowed samples n = (25 n1 + 16 n2) mod 400, packed f32x2 over two frames
-//   stage 2  per warp: one k2 slot for 32 frame pairs; 16-point complex DFT over n1, |X|^2
-//   mel      per warp: a run of filters for 32 frame pairs; sparse gather; mel POWER retained in
+//   stage 2  per HALF warp: one k2 slot for 16 frame pairs; 16-point complex DFT over n1, |X|^2
+//   mel      per warp: a run of <= 16 filters, lane = frame; sparse gather; mel POWER retained in
 //            TENSOR MEMORY (tcgen05.st), running max in registers
 //
-// with the prime-factor index maps of fft_pfa.cuh (no twiddles between the stages).  All arithmetic on
-// the data path is FADD2 / FMUL2 / FFMA2 on (frame a, frame b) pairs with immediate constants.
-// When the clip is done the 6 CTAs exchange their maxima through distributed shared memory
+// with the prime-factor index maps of fft_pfa.cuh (no twiddles between the stages).  The FFT
+// arithmetic is FADD2 / FMUL2 / FFMA2 on (frame a, frame b) pairs with immediate constants.
+// The two groups share nothing but the cluster barrier: they are started out of phase, so the
+// shared-memory-bound passes of one group (loads / stores around each FFT) run under the FMA-bound
+// passes of the other -- one group alone serialises them (measured: LDS.64 costs two shared-memory
+// cycles per SM, FADD2 two FMA-pipe cycles per scheduler; tools/ubench_issue.cu).
+// When the clip is done the 12 virtual CTAs exchange their maxima through distributed shared memory
 // (one cluster barrier), and a single pass reads the retained mel power back (tcgen05.ld) and writes
 // (max(log10(max(p,1e-10)), gmax - 8) + 4) / 4 -- the features touch HBM exactly once.
 //
-// Shared memory (bytes):  raw 42,880 | Y 102,528 | P 51,456 | mbarrier + scratch 256
+// Shared memory (bytes):  raw 2 x 22,400 | Y 2 x 53,376 | P 2 x 26,624 | mbarriers + scratch 512
 #pragma once
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
@@ -50,47 +55,64 @@ using fused::vadd; using fused::vsub; using fused::vmul; using fused::vfma; usin
 namespace wlm {
 namespace fused {
 
-constexpr int kTile = 64;                 // frames per tile
-constexpr int kWarps = 16;
+constexpr int kGroups = 2;                // independent warp groups per CTA
+constexpr int kGroupWarps = 8;
+constexpr int kGroupThreads = kGroupWarps * 32;
+constexpr int kWarps = kGroups * kGroupWarps;
 constexpr int kThreads = kWarps * 32;
-constexpr int kTilesPerClip = (kNFrames + kTile - 1) / kTile;  // 47
-constexpr int kRegion = 31 * kHop + kNfft;                     // 5360 samples: frames 0..31 of a half tile
-constexpr int kRegionStep = 32 * kHop;                         // 5120: region B starts 32 frames later
-constexpr int kRawFloats = 2 * kRegion;                        // 10720 (5360 = 16 mod 32: regions 16 banks apart)
-constexpr int kTileSamples = 63 * kHop + kNfft;                // 10480
-constexpr int kYStride = 801;                                  // float2 per n1 row (25*32 + 1: odd)
-constexpr int kYFloat2 = 16 * kYStride;
-constexpr int kPFloat2 = kNFreq * 32;
+constexpr int kTile = 32;                 // frames per half-tile (the unit of work of one group)
+constexpr int kPairs = kTile / 2;         // 16 frame pairs
+constexpr int kTilesPerClip = (kNFrames + kTile - 1) / kTile;  // 94
+constexpr int kSubFrames = 16;                                 // frames per raw sub-region
+constexpr int kSubLen = (kSubFrames - 1) * kHop + kNfft;       // 2800 samples (= 16 mod 32: sub-regions 16 banks apart)
+constexpr int kSubStep = kSubFrames * kHop;                    // 2560: sub-region 1 starts 16 frames later
+constexpr int kRawFloats = 2 * kSubLen;                        // 5600 per group
+constexpr int kTileSamples = (kTile - 1) * kHop + kNfft;       // 5360
+static_assert(kSubLen % 32 == 16, "the two sub-regions must sit 16 banks apart");
+static_assert(kSubStep + kSubLen == kTileSamples, "sub-regions cover the half-tile");
 
-constexpr int kSmemRaw = kRawFloats * 4;        // 42,880
-constexpr int kSmemY = kYFloat2 * 8;            // 102,528
-constexpr int kSmemP = kPFloat2 * 8;            // 51,456
-constexpr int kSmemBytes = kSmemRaw + kSmemY + kSmemP + 256;
+// Y (stage 1 -> stage 2), per group: [n1][26 components][16 pairs] float2 (two frames); slot s reads components
+// 2 s (Re) and 2 s + 1 (Im): component 0 = Re Y[k2=0], component 1 = zeros (written once, slot 0 is purely real).
+// (A [n1][pair][component] layout with 128-bit accesses was measured: ptxas assembles every STS.128 with four MOVs.)
+constexpr int kYComps = 2 * fft::kNumSlots;                    // 26
+constexpr int kYN1 = kYComps * kPairs + 1;                     // 417 float2 per n1 row (odd: 16 lanes x 8 B conflict-free)
+constexpr int kYFloat2 = 16 * kYN1;
+// P (stage 2 -> mel), per group: [row = slot * 16 + position in the FFT16 output][32 frames] float
+constexpr int kPRows = fft::kNumSlots * 16;                    // 208 (201 distinct bins; slot 0 holds each of its bins twice)
+constexpr int kPFloats = kPRows * kTile;
+
+constexpr int kSmemRaw = kRawFloats * 4;        // 22,400
+constexpr int kSmemY = kYFloat2 * 8;            // 53,376
+constexpr int kSmemP = kPFloats * 4;            // 26,624
+constexpr int kSmemGroup = kSmemRaw + kSmemY + kSmemP;
+constexpr int kSmemMisc = 512;
+constexpr int kSmemBytes = kGroups * kSmemGroup + kSmemMisc;
+static_assert(kSmemRaw % 128 == 0 && kSmemY % 128 == 0 && kSmemP % 128 == 0, "buffers stay 128-byte aligned");
 
 constexpr int kCluster = 6;                     // CTAs per clip: 22 co-resident clusters = 132 of 148 SMs (size 8: 15 = 120)
-constexpr int kMaxTilesPerCta = (kTilesPerClip + kCluster - 1) / kCluster;   // 8
-constexpr int kMaxFiltersPerWarp = 8;           // 16 warps x 8 >= 128 mels
+constexpr int kVCluster = kCluster * kGroups;   // 12 virtual CTAs per clip
+constexpr int kMaxTilesPerGroup = (kTilesPerClip + kVCluster - 1) / kVCluster;   // 8
+constexpr int kMaxFiltersPerWarp = 16;          // 8 warps x 16 >= 128 mels
 constexpr int kMaxGroupBins = 16;               // bins between two adjacent filter centres
-constexpr int kTmemColsPerTile = 2 * kMaxFiltersPerWarp;                      // 16 (two frames per filter)
-constexpr int kTmemColsPerWarp = kMaxTilesPerCta * kTmemColsPerTile;          // 128; 4 warps per lane quarter = 512 columns
+constexpr int kTmemColsPerTile = kMaxFiltersPerWarp;                          // 16 (lane = frame)
+constexpr int kTmemColsPerWarp = kMaxTilesPerGroup * kTmemColsPerTile;        // 128; 4 warps per lane quarter = 512 columns
+constexpr int kS2Warps = (fft::kNumSlots + 1) / 2;                            // 7 warps of a group run stage 2 (two slots each)
 static_assert(4 * kTmemColsPerWarp <= 512, "the retained mel power must fit the 512 TMEM columns");
-static_assert(kCluster <= 8, "max reduction over the cluster uses 8 lanes");
+static_assert(kVCluster <= 32, "max reduction over the cluster uses one warp");
 
 // Everything the kernel reads with warp-uniform indices, passed by value (constant bank).
 //
 // Mel projection: FFT bin k adds w_lo[k] P[k] to filter lo[k] and w_hi[k] P[k] to filter lo[k]+1
 // (host-built from the caller's dense table, weights bit-identical).  Bins with the same lo[k] form
-// a "group" (the bins between two adjacent filter centres).  Warp w owns filters
+// a "group" (the bins between two adjacent filter centres).  Warp w of a warp group owns filters
 // [m0, m0+nf) and walks groups g = 0..nf, group g = bins [gb[g], gb[g+1]) with lo = m0-1+g:
 //     filter m0+q  =  sum_{k in group q} w_hi[k] P[k]  +  sum_{k in group q+1} w_lo[k] P[k]
 struct KernelTables {
-    float4 w4[kNFreq + 3];                          // (w_lo, w_lo, w_hi, w_hi) per bin
-    int16_t gb[kWarps][kMaxFiltersPerWarp + 2];     // group boundaries (bin indices)
-    int16_t m0[kWarps];                             // first filter of warp w
-    int16_t nf[kWarps];                             // number of filters of warp w (<= 8)
-    // stage 2: per k2 slot, float2 offsets into Y (component) and into P (output bin) per FFT16 output
-    int32_t slot_comp_off[16];                      // comp * 32
-    int32_t slot_pbin_off[13][16];                  // BYTE offset of output_bin(k1, k2) in P, indexed by cfft16 array position
+    float2 w2[kNFreq + 3];                               // (w_lo, w_hi) per bin
+    int16_t prow[kNFreq + 3];                            // row of P that holds bin k
+    int16_t gb[kGroupWarps][kMaxFiltersPerWarp + 2];     // group boundaries (bin indices)
+    int16_t m0[kGroupWarps];                             // first filter of warp w
+    int16_t nf[kGroupWarps];                             // number of filters of warp w (<= 16)
     int16_t n_mels;
 };
 using MelParams = KernelTables;
@@ -113,7 +135,10 @@ inline int build_tables(const MelSparse& sp, int n_mels, Tables* t, int* variant
     KernelTables& mp = t->mel;
     memset(&mp, 0, sizeof(mp));
     mp.n_mels = (int16_t)n_mels;
-    for (int k = 0; k < kNFreq; ++k) mp.w4[k] = make_float4(sp.w_lo[k], sp.w_lo[k], sp.w_hi[k], sp.w_hi[k]);
+    for (int k = 0; k < kNFreq; ++k) {
+        mp.w2[k] = make_float2(sp.w_lo[k], sp.w_hi[k]);
+        mp.prow[k] = (int16_t)fft::row_of_bin(k);
+    }
     // first bin of every group: gstart[v] = first k with lo[k] >= v - 1   (v = lo + 1 in 0..n_mels)
     int gstart[kMaxMels + 2];
     {
@@ -131,15 +156,15 @@ inline int build_tables(const MelSparse& sp, int n_mels, Tables* t, int* variant
     bool same = baked_g != nullptr;
     for (int v = 0; same && v <= n_mels + 1; ++v) same = gstart[v] == baked_g[v];
     if (same) *variant = n_mels;
-    // contiguous filter runs per warp, balanced on issue slots: ~4 per bin of the two groups a filter
-    // touches (shared with its neighbour) + ~12 per filter
-    auto cost = [&](int m) { return 12.0 + 2.0 * (gstart[m + 2] - gstart[m]); };
+    // contiguous filter runs per warp, balanced on issue slots: ~3 per bin of the two groups a filter
+    // touches (shared with its neighbour) + ~7 per filter
+    auto cost = [&](int m) { return 7.0 + 1.5 * (gstart[m + 2] - gstart[m]); };
     double total = 0;
     for (int m = 0; m < n_mels; ++m) total += cost(m);
     int m = 0;
     double acc = 0;
-    for (int w = 0; w < kWarps; ++w) {
-        const double target = total * (w + 1) / kWarps;
+    for (int w = 0; w < kGroupWarps; ++w) {
+        const double target = total * (w + 1) / kGroupWarps;
         int cnt = 0;
         mp.m0[w] = (int16_t)m;
         if (same) {   // partition baked into the unrolled kernel
@@ -148,7 +173,7 @@ inline int build_tables(const MelSparse& sp, int n_mels, Tables* t, int* variant
             m = mp.m0[w] + cnt;
         }
         while (!same && m < n_mels && cnt < kMaxFiltersPerWarp) {
-            const bool must_take = n_mels - m > (kWarps - 1 - w) * kMaxFiltersPerWarp;   // the rest could not hold them
+            const bool must_take = n_mels - m > (kGroupWarps - 1 - w) * kMaxFiltersPerWarp;   // the rest could not hold them
             if (!must_take && cnt > 0 && acc + 0.5 * cost(m) > target) break;
             acc += cost(m);
             ++m;
@@ -162,11 +187,6 @@ inline int build_tables(const MelSparse& sp, int n_mels, Tables* t, int* variant
         }
     }
     if (m < n_mels) return -1;
-    for (int s2 = 0; s2 < fft::kNumSlots; ++s2) {
-        mp.slot_comp_off[s2] = fft::kSlotComp[s2] * 32;
-        for (int k1 = 0; k1 < 16; ++k1)
-            mp.slot_pbin_off[s2][fft::fft16_slot_of_k1(k1)] = fft::output_bin(k1, fft::kSlotK2[s2]) * 32 * 8;
-    }
     return 0;
 }
 
@@ -183,7 +203,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "{\n"
         ".reg .pred p;\n"
         "WAIT_%=:\n"
-#ifdef WLM_OPT_HINT
+        #ifdef WLM_OPT_HINT
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n"   /* suspend-time hint: sleep, do not spin */
 #else
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
@@ -191,6 +211,22 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "@p bra DONE_%=;\n"
         "bra WAIT_%=;\n"
         "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+// same, acquiring at cluster scope: the data the barrier guards was written by other CTAs of the cluster
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAITC_%=:\n"
+        #ifdef WLM_OPT_HINT
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1, 0x989680;\n"
+#else
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+#endif
+        "@p bra DONEC_%=;\n"
+        "bra WAITC_%=;\n"
+        "DONEC_%=:\n"
         "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
@@ -201,6 +237,10 @@ __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// named barrier over the 256 threads of one warp group (id 1 / 2; 0 is __syncthreads)
+__device__ __forceinline__ void group_sync(int grp) {
+    asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(kGroupThreads) : "memory");
+}
 __device__ __forceinline__ float lg2_approx(float x) {
     float y;
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -210,7 +250,7 @@ __device__ __forceinline__ float lg2_approx(float x) {
 // ---- tensor memory (tcgen05) -------------------------------------------------------------------
 // The retained mel power never needs a tensor core; TMEM is used as 256 KB of per-SM scratch so the
 // clip's features can wait on-chip for the cluster-wide max.  Warp w may only touch TMEM lanes
-// [32 (w & 3), +32): lane i of the warp <-> TMEM lane 32 (w & 3) + i, i.e. one frame pair per lane.
+// [32 (w & 3), +32): lane i of the warp <-> TMEM lane 32 (w & 3) + i, i.e. one frame per lane.
 __device__ __forceinline__ void tmem_alloc_512(uint32_t smem_dst) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_dst) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -218,14 +258,11 @@ __device__ __forceinline__ void tmem_alloc_512(uint32_t smem_dst) {
 __device__ __forceinline__ void tmem_dealloc_512(uint32_t taddr) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(taddr) : "memory");
 }
-__device__ __forceinline__ void tmem_st_x2(uint32_t taddr, float a, float b) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "f"(a), "f"(b) : "memory");
-}
-__device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const float2 (&v)[8]) {
+__device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const float (&v)[16]) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-        ::"r"(taddr), "f"(v[0].x), "f"(v[0].y), "f"(v[1].x), "f"(v[1].y), "f"(v[2].x), "f"(v[2].y), "f"(v[3].x), "f"(v[3].y),
-          "f"(v[4].x), "f"(v[4].y), "f"(v[5].x), "f"(v[5].y), "f"(v[6].x), "f"(v[6].y), "f"(v[7].x), "f"(v[7].y) : "memory");
+        ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]),
+          "f"(v[8]), "f"(v[9]), "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15]) : "memory");
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, float (&r)[16]) {
@@ -237,9 +274,9 @@ __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, float (&r)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// ---- clip / tile bookkeeping (all values CTA-uniform) ---------------------------------------------
+// ---- clip / tile bookkeeping (all values group-uniform) -------------------------------------------
 struct ClipCtx {
-    int b, len, n_act;     // clip index, valid samples (<= 480000), tiles that contain any real sample
+    int b, len, n_act;     // clip index, valid samples (<= 480000), half-tiles that contain any real sample
     int64_t base;          // element offset of the clip in the PCM buffer
 };
 
@@ -250,13 +287,13 @@ __device__ __forceinline__ ClipCtx clip_ctx(const ClipArgs& a, int b) {
     int len = a.lengths ? a.lengths[b] : a.dense_len;
     if (!a.offsets) len = static_cast<int>(min(static_cast<int64_t>(len), a.row_stride));
     c.len = max(0, min(len, kNSamples));
-    // tile t starts at sample 10240 t - 200: active iff that is < len
+    // half-tile t starts at sample 5120 t - 200: active iff that is < len
     c.n_act = min(kTilesPerClip, (c.len + kNfft / 2 + kTile * kHop - 1) / (kTile * kHop));
     return c;
 }
 __device__ __forceinline__ int tile_s0(int tile) { return tile * (kTile * kHop) - kNfft / 2; }
 
-// issued by one thread: both regions of the tile, valid sample range only
+// issued by one thread: both sub-regions of the half-tile, valid sample range only
 __device__ __forceinline__ void tile_issue_tma(const ClipArgs& a, const ClipCtx& c, int tile, float* raw, uint32_t bar) {
     const int s0 = tile_s0(tile);
     const int esz = a.pcm_format == WLM_PCM_I16 ? 2 : 4;
@@ -266,9 +303,9 @@ __device__ __forceinline__ void tile_issue_tma(const ClipArgs& a, const ClipCtx&
     int lo[2], n[2];
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
-        const int s_lo = s0 + r * kRegionStep;
+        const int s_lo = s0 + r * kSubStep;
         lo[r] = max(s_lo, 0);
-        const int hi = min(s_lo + kRegion, len_up);
+        const int hi = min(s_lo + kSubLen, len_up);
         n[r] = max(hi - lo[r], 0);
         total += static_cast<uint32_t>(n[r]) * esz;
     }
@@ -276,145 +313,174 @@ __device__ __forceinline__ void tile_issue_tma(const ClipArgs& a, const ClipCtx&
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
         if (n[r] <= 0) continue;
-        const int s_lo = s0 + r * kRegionStep;
+        const int s_lo = s0 + r * kSubStep;
         const char* src = static_cast<const char*>(a.pcm) + (c.base + lo[r]) * esz;
         uint32_t dst;
-        if (esz == 4) dst = smem_u32(raw) + static_cast<uint32_t>(r * kRegion + (lo[r] - s_lo)) * 4u;
-        else dst = smem_u32(raw) + static_cast<uint32_t>(kRegion) * 4u + static_cast<uint32_t>(r * kRegion + (lo[r] - s_lo)) * 2u;
+        if (esz == 4) dst = smem_u32(raw) + static_cast<uint32_t>(r * kSubLen + (lo[r] - s_lo)) * 4u;
+        else dst = smem_u32(raw) + static_cast<uint32_t>(kSubLen) * 4u + static_cast<uint32_t>(r * kSubLen + (lo[r] - s_lo)) * 2u;
         tma_bulk_g2s(dst, src, static_cast<uint32_t>(n[r]) * esz, bar);
     }
 }
 
-// int16 -> float32 expansion in place (staging sits in the byte range of region B) + reflect /
+// int16 -> float32 expansion in place (staging sits in the byte range of sub-region 1) + reflect /
 // zero-fill patching of every position outside [0, len).  Only edge tiles and int16 input pay.
-__device__ __forceinline__ void tile_fixup(const ClipArgs& a, const ClipCtx& c, int tile, float* raw) {
-    const int tid = threadIdx.x;
+// Runs on the 256 threads of one group (tg = thread index inside the group).
+__device__ __forceinline__ void tile_fixup(const ClipArgs& a, const ClipCtx& c, int tile, float* raw, int grp, int tg) {
     const int s0 = tile_s0(tile);
     if (a.pcm_format == WLM_PCM_I16) {
-        const int16_t* st = reinterpret_cast<const int16_t*>(raw + kRegion);
+        const int16_t* st = reinterpret_cast<const int16_t*>(raw + kSubLen);
         constexpr float kScale = 1.0f / 32768.0f;
-        for (int i = tid; i < kRegion; i += kThreads) raw[i] = static_cast<float>(st[i]) * kScale;
-        float tmp[(kRegion + kThreads - 1) / kThreads];
+        constexpr int kPer = (kSubLen + kGroupThreads - 1) / kGroupThreads;
+        for (int i = tg; i < kSubLen; i += kGroupThreads) raw[i] = static_cast<float>(st[i]) * kScale;
+        float tmp[kPer];
 #pragma unroll
-        for (int j = 0; j < (kRegion + kThreads - 1) / kThreads; ++j) {
-            const int i = tid + j * kThreads;
-            tmp[j] = i < kRegion ? static_cast<float>(st[kRegion + i]) * kScale : 0.f;
+        for (int j = 0; j < kPer; ++j) {
+            const int i = tg + j * kGroupThreads;
+            tmp[j] = i < kSubLen ? static_cast<float>(st[kSubLen + i]) * kScale : 0.f;
         }
-        __syncthreads();
+        group_sync(grp);
 #pragma unroll
-        for (int j = 0; j < (kRegion + kThreads - 1) / kThreads; ++j) {
-            const int i = tid + j * kThreads;
-            if (i < kRegion) raw[kRegion + i] = tmp[j];
+        for (int j = 0; j < kPer; ++j) {
+            const int i = tg + j * kGroupThreads;
+            if (i < kSubLen) raw[kSubLen + i] = tmp[j];
         }
-        __syncthreads();
+        group_sync(grp);
     }
-    if (s0 < 0 || s0 + kTileSamples > c.len) {
-        for (int idx = tid; idx < kRawFloats; idx += kThreads) {
-            const int r = idx >= kRegion ? 1 : 0;
-            const int s = s0 + r * kRegionStep + (idx - r * kRegion);
-            if (s >= 0 && s < c.len) continue;
-            // reflect of the zero-padded 480000 buffer (torch.stft center=True, TF-FE:149)
-            const int sr = s < 0 ? -s : (s >= kNSamples ? 2 * (kNSamples - 1) - s : s);
-            float v = 0.f;
-            if (sr >= 0 && sr < c.len) {
-                const int u = sr - s0;
-                if (u >= 0 && u < kTileSamples) v = raw[u < kRegion ? u : kRegion + (u - kRegionStep)];
+    // Only the positions outside [0, len) are touched (a scan of the whole buffer cost ~8k cycles on the first
+    // half-tile of every clip, and the other 11 virtual CTAs of the cluster wait for that one at the clip's end).
+    if (s0 < 0) {   // first half-tile: s = idx - 200 < 0 reflects to sample 200 - idx (torch.stft center=True, TF-FE:149)
+        for (int idx = tg; idx < -s0; idx += kGroupThreads) {
+            const int sr = -(s0 + idx);
+            raw[idx] = sr < c.len ? raw[sr - s0] : 0.f;        // (sr - s0 <= 400 < kSubLen: same sub-region)
+        }
+    }
+    if (s0 + kTileSamples > c.len) {   // the half-tile runs past the clip: zero padding, reflected at sample 480000
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int s_lo = s0 + r * kSubStep;
+            for (int i = max(c.len - s_lo, 0) + tg; i < kSubLen; i += kGroupThreads) {
+                const int s = s_lo + i;
+                float v = 0.f;
+                if (s >= kNSamples) {
+                    const int sr = 2 * (kNSamples - 1) - s;
+                    const int u = sr - s0;
+                    if (sr < c.len && u >= 0) v = raw[u < kSubLen ? u : kSubLen + (u - kSubStep)];
+                }
+                raw[r * kSubLen + i] = v;
             }
-            raw[idx] = v;
         }
-        __syncthreads();
     }
+    if (s0 < 0 || s0 + kTileSamples > c.len) group_sync(grp);
 }
 
 // ---- stage 1 ----------------------------------------------------------------------------------
-// warp w, lane (n1 = lane & 15, g = lane >> 4): the two ADJACENT frames 32 g + 2 w, 32 g + 2 w + 1 of the tile
-// (pair index 16 g + w = lane of the later stages, whose outputs are then one float2 per lane).
+// warp wg of the group, lane (n1 = lane & 15, sub = lane >> 4): the two ADJACENT frames 16 sub + 2 wg, + 1 of the
+// half-tile (pair index 8 sub + wg).  The sample index (25 n1 + 16 t) mod 400 wraps for t >= tw(n1); with
+// wrap_thr(t) = the first n1 that wraps at t, the select is one compare against a compile-time constant.
+__host__ __device__ constexpr int wrap_tw(int n1) { return n1 == 0 ? 25 : (kNfft - 25 * n1 + 15) / 16; }
+__host__ __device__ constexpr int wrap_thr(int t) {
+    for (int n1 = 0; n1 < 16; ++n1)
+        if (wrap_tw(n1) <= t) return n1;
+    return 16;
+}
 // `loaded()` runs once the warp no longer needs the raw buffer, `before_store()` just before Y is written.
-template <class Loaded, class BeforeStore>
-__device__ __forceinline__ void stage1(const float* raw, float2* Y, const float (&wv)[25], int tw, int warp, int lane,
-                                       Loaded loaded, BeforeStore before_store) {
-    const int n1 = lane & 15, g = lane >> 4;
-    const float* p0 = raw + g * kRegion + 2 * kHop * warp + 25 * n1;
-    const float* p1 = p0 - kNfft;
-    V2 y[25];
-#pragma unroll
-    for (int t = 0; t < 25; ++t) {
-        const float* p = (t >= tw) ? p1 : p0;
-        const float xa = p[16 * t], xb = p[16 * t + kHop];
-        y[t] = mk(xa * wv[t], xb * wv[t]);
+template <int T>
+struct S1Load {   // samples t = T .. 24 of both frames: one compare + select per distinct wrap threshold, then LDS [reg + imm]
+    static __device__ __forceinline__ void run(uint32_t a0, uint32_t a1, uint32_t n1, const float (&wv)[25], V2 (&y)[25]) {
+        constexpr int thr = wrap_thr(T);
+        uint32_t at;
+        if (thr >= 16) at = a0;
+        else if (thr <= 0) at = a1;
+        else asm("{\n.reg .pred p;\nsetp.ge.u32 p, %1, %2;\nselp.b32 %0, %3, %4, p;\n}" : "=r"(at) : "r"(n1), "n"(thr), "r"(a1), "r"(a0));
+        float xa, xb;
+        asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(xa) : "r"(at), "n"(64 * T));
+        asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(xb) : "r"(at), "n"(64 * T + 4 * kHop));
+        y[T] = mk(xa * wv[T], xb * wv[T]);
+        S1Load<T + 1>::run(a0, a1, n1, wv, y);
     }
+};
+template <>
+struct S1Load<25> {
+    static __device__ __forceinline__ void run(uint32_t, uint32_t, uint32_t, const float (&)[25], V2 (&)[25]) {}
+};
+
+template <class Loaded, class BeforeStore>
+__device__ __forceinline__ void stage1(const float* raw, float2* Y, const float (&wv)[25], int wg, int lane,
+                                       Loaded loaded, BeforeStore before_store) {
+    const int n1 = lane & 15, sub = lane >> 4;
+    const uint32_t a0 = smem_u32(raw + sub * kSubLen + 2 * kHop * wg + 25 * n1);
+    V2 y[25];
+    S1Load<0>::run(a0, a0 - 4u * kNfft, static_cast<uint32_t>(n1), wv, y);
     loaded();      // (fence inside: every LDS above has been performed)
     V2 out[25];
-    fft::rfft25<V2>(y, out);
-    before_store();
-    float2* yo = Y + n1 * kYStride + (warp + 16 * g);
+#ifdef WLM_KO_S1FFT   /* diagnostic knock-out: results are wrong */
 #pragma unroll
-    for (int c = 0; c < 25; ++c) yo[c * 32] = out[c].v;
+    for (int c = 0; c < 25; ++c) out[c] = y[c];
+#else
+    fft::rfft25<V2>(y, out);
+#endif
+    before_store();
+    float2* yo = Y + n1 * kYN1 + (8 * sub + wg);
+    yo[0] = out[0].v;
+#pragma unroll
+    for (int c = 1; c < 25; ++c) yo[(c + 1) * kPairs] = out[c].v;     // slot s >= 1: Re at component 2 s, Im at 2 s + 1
 }
 
 // ---- stage 2 ----------------------------------------------------------------------------------
-// warp = k2 slot (uniform), lane = frame pair.  One code path for all 13 slots: the slot only selects
-// table offsets, so every warp runs the same instructions (a 13-way templated version thrashed the
-// instruction cache: 28 % of issue stalls were "no instruction").
+// half warp = one k2 slot (lane-varying: only two base addresses depend on it), lane & 15 = frame pair.
+// The power of FFT16 output position i goes to row 16 slot + i of P (fft::row_of_bin inverts that for the mel stage).
 // `loaded()` runs once Y has been read, `before_store()` just before P is written.
 template <class Loaded, class BeforeStore>
-__device__ __forceinline__ void stage2(const KernelTables& kt, const float2* Y, float2* P, int slot, int lane,
-                                       Loaded loaded, BeforeStore before_store) {
-    const float2* yl = Y + kt.slot_comp_off[slot] + lane;
+__device__ __forceinline__ void stage2(const float2* Y, float* P, int slot, int pair, Loaded loaded, BeforeStore before_store) {
+    const float2* yl = Y + 2 * slot * kPairs + pair;
     V2 xr[16], xi[16];
 #pragma unroll
     for (int n1 = 0; n1 < 16; ++n1) {
-        xr[n1].v = yl[n1 * kYStride];
-        xi[n1].v = yl[n1 * kYStride + 32];      // slot 0 (k2 = 0, purely real Y): fetches component 1, discarded below
+        xr[n1].v = yl[n1 * kYN1];
+        xi[n1].v = yl[n1 * kYN1 + kPairs];       // slot 0 (k2 = 0, purely real Y): the zero component
     }
     loaded();
-    if (slot == 0) {
-#pragma unroll
-        for (int n1 = 0; n1 < 16; ++n1) xi[n1] = mk(0.f, 0.f);
-    }
+#ifndef WLM_KO_S2FFT
     fft::cfft16<V2>(xr, xi);
+#endif
     before_store();
-    char* pl = reinterpret_cast<char*>(P + lane);
+    float2* pl = reinterpret_cast<float2*>(P + slot * 16 * kTile) + pair;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-        // slot 0 writes bins 25 j twice (k1 and 16-k1 are conjugates): same thread, same value class
         const V2 pw = vfma(xr[i], xr[i], vmul(xi[i], xi[i]));
-        *reinterpret_cast<float2*>(pl + kt.slot_pbin_off[slot][i]) = pw.v;
+        pl[i * kPairs] = pw.v;
     }
 }
 
-// lane = frame pair of the tile: frames (2 lane, 2 lane + 1)
-__device__ __forceinline__ int pair_frame_a(int lane) { return 2 * lane; }
-
 // ---- mel stage ------------------------------------------------------------------------------------
-// One warp, its run of <= 8 filters, 32 frame pairs.  Groups of bins between adjacent filter centres
+// One warp, its run of <= 16 filters, lane = frame.  Groups of bins between adjacent filter centres
 // are walked once: every P value is loaded once and feeds the falling side of one filter and the
-// rising side of the next (two independent FFMA2 chains).  The group loop is unrolled (static
-// register indices for the 8 outputs); inside, a fall-through switch on the group length gives one
-// straight-line copy of the 16 possible terms.  The POWER goes to tensor memory (16 columns:
-// 8 filters x two frames); log10 is monotone, so the running max is kept on the power.
+// rising side of the next (two independent FFMA chains, weights straight from the constant bank).
+// The POWER goes to tensor memory (16 columns = 16 filters); log10 is monotone, so the running max
+// is kept on the power.
 #define WLM_MEL_TERM(i)                                                            \
     case (i) + 1: {                                                                \
-        const float4 w = ww[i];                                                    \
-        const float2 pv = pp[(i) * 32];                                            \
-        A = __ffma2_rn(pv, make_float2(w.z, w.w), A);                              \
-        Bq = __ffma2_rn(pv, make_float2(w.x, w.y), Bq);                            \
+        const float2 w = ww[i];                                                    \
+        const float pv = pl[pr[i] * kTile];                                        \
+        A = fmaf(pv, w.y, A);                                                      \
+        Bq = fmaf(pv, w.x, Bq);                                                    \
     }
 
-__device__ __forceinline__ float2 mel_stage(const KernelTables& kt, const float2* P, int warp, int lane, uint32_t tcol) {
-    const int nf = kt.nf[warp];
-    const float2* pl = P + lane;
-    float2 out[kMaxFiltersPerWarp];
+// table-driven variant (any bank that fits the sparse form)
+__device__ __forceinline__ float mel_stage(const KernelTables& kt, const float* P, int wg, int lane, uint32_t tcol) {
+    const int nf = kt.nf[wg];
+    const float* pl = P + lane;
+    float out[kMaxFiltersPerWarp];
 #pragma unroll
-    for (int q = 0; q < kMaxFiltersPerWarp; ++q) out[q] = make_float2(0.f, 0.f);
+    for (int q = 0; q < kMaxFiltersPerWarp; ++q) out[q] = 0.f;
 #pragma unroll
     for (int g = 0; g <= kMaxFiltersPerWarp; ++g) {
         if (g <= nf) {
-            const int k0 = kt.gb[warp][g];
-            const int n = kt.gb[warp][g + 1] - k0;
-            const float2* pp = pl + k0 * 32;
-            const float4* ww = kt.w4 + k0;
-            float2 A = make_float2(0.f, 0.f), Bq = make_float2(0.f, 0.f);
+            const int k0 = kt.gb[wg][g];
+            const int n = kt.gb[wg][g + 1] - k0;
+            const int16_t* pr = kt.prow + k0;
+            const float2* ww = kt.w2 + k0;
+            float A = 0.f, Bq = 0.f;
             switch (n) {
                 WLM_MEL_TERM(15) WLM_MEL_TERM(14) WLM_MEL_TERM(13) WLM_MEL_TERM(12)
                 WLM_MEL_TERM(11) WLM_MEL_TERM(10) WLM_MEL_TERM(9) WLM_MEL_TERM(8)
@@ -422,25 +488,22 @@ __device__ __forceinline__ float2 mel_stage(const KernelTables& kt, const float2
                 WLM_MEL_TERM(3) WLM_MEL_TERM(2) WLM_MEL_TERM(1) WLM_MEL_TERM(0)
                 default: break;
             }
-            if (g < kMaxFiltersPerWarp) out[g] = A;                      // rising side of filter m0+g
-            if (g > 0) out[g - 1] = __fadd2_rn(out[g - 1], Bq);          // falling side of filter m0+g-1
+            if (g < kMaxFiltersPerWarp) out[g] = A;          // rising side of filter m0+g
+            if (g > 0) out[g - 1] += Bq;                     // falling side of filter m0+g-1
         }
     }
     tmem_st_x16(tcol, out);
-    float2 mx = make_float2(0.f, 0.f);
+    float mx = 0.f;
 #pragma unroll
     for (int q = 0; q < kMaxFiltersPerWarp; ++q)
-        if (q < nf) {
-            mx.x = fmaxf(mx.x, out[q].x);
-            mx.y = fmaxf(mx.y, out[q].y);
-        }
+        if (q < nf) mx = fmaxf(mx, out[q]);
     return mx;
 }
 #undef WLM_MEL_TERM
 
-// Unrolled variant for the two Whisper banks: group boundaries and the warp's filter run are
-// compile-time constants (mel_structure.inc), so the stage is straight-line code -- one LDS.64 and
-// one 16-byte constant load per bin, FFMA2 straight into statically indexed accumulators.
+// Unrolled variant for the two Whisper banks: group boundaries, the warp's filter run and the P row of
+// every bin are compile-time constants (mel_structure.inc, fft::row_of_bin), so the stage is
+// straight-line code -- one LDS and two FFMA with constant-bank weights per bin.
 template <int NMELS> struct MelFixed;
 template <> struct MelFixed<80> {
     static __device__ __forceinline__ constexpr int gstart(int v) { return kMelGstart80[v]; }
@@ -454,36 +517,33 @@ template <> struct MelFixed<128> {
 };
 
 template <int NMELS, int W>
-__device__ __forceinline__ float2 mel_fixed_warp(const KernelTables& kt, const float2* P, int lane, uint32_t tcol) {
+__device__ __forceinline__ float mel_fixed_warp(const KernelTables& kt, const float* P, int lane, uint32_t tcol) {
     using S = MelFixed<NMELS>;
     constexpr int nf = S::nf(W), m0 = S::m0(W);
-    const float2* pl = P + lane;
-    float2 out[kMaxFiltersPerWarp];
+    const float* pl = P + lane;
+    float out[kMaxFiltersPerWarp];
 #pragma unroll
-    for (int q = 0; q < kMaxFiltersPerWarp; ++q) out[q] = make_float2(0.f, 0.f);
+    for (int q = 0; q < kMaxFiltersPerWarp; ++q) out[q] = 0.f;
 #pragma unroll
     for (int g = 0; g <= nf; ++g) {
 #pragma unroll
         for (int k = S::gstart(m0 + g); k < S::gstart(m0 + g + 1); ++k) {
-            const float4 w = kt.w4[k];
-            const float2 pv = pl[k * 32];
-            if (g < nf) out[g] = __ffma2_rn(pv, make_float2(w.z, w.w), out[g]);            // rising side of m0+g
-            if (g > 0) out[g - 1] = __ffma2_rn(pv, make_float2(w.x, w.y), out[g - 1]);     // falling side of m0+g-1
+            const float2 w = kt.w2[k];
+            const float pv = pl[fft::row_of_bin(k) * kTile];
+            if (g < nf) out[g] = fmaf(pv, w.y, out[g]);            // rising side of m0+g
+            if (g > 0) out[g - 1] = fmaf(pv, w.x, out[g - 1]);     // falling side of m0+g-1
         }
     }
     tmem_st_x16(tcol, out);
-    float2 mx = make_float2(0.f, 0.f);
+    float mx = 0.f;
 #pragma unroll
-    for (int q = 0; q < nf; ++q) {
-        mx.x = fmaxf(mx.x, out[q].x);
-        mx.y = fmaxf(mx.y, out[q].y);
-    }
+    for (int q = 0; q < nf; ++q) mx = fmaxf(mx, out[q]);
     return mx;
 }
 
 template <int NMELS>
-__device__ __forceinline__ float2 mel_fixed(const KernelTables& kt, const float2* P, int warp, int lane, uint32_t tcol) {
-    switch (warp) {
+__device__ __forceinline__ float mel_fixed(const KernelTables& kt, const float* P, int wg, int lane, uint32_t tcol) {
+    switch (wg) {
         case 0: return mel_fixed_warp<NMELS, 0>(kt, P, lane, tcol);
         case 1: return mel_fixed_warp<NMELS, 1>(kt, P, lane, tcol);
         case 2: return mel_fixed_warp<NMELS, 2>(kt, P, lane, tcol);
@@ -491,15 +551,7 @@ __device__ __forceinline__ float2 mel_fixed(const KernelTables& kt, const float2
         case 4: return mel_fixed_warp<NMELS, 4>(kt, P, lane, tcol);
         case 5: return mel_fixed_warp<NMELS, 5>(kt, P, lane, tcol);
         case 6: return mel_fixed_warp<NMELS, 6>(kt, P, lane, tcol);
-        case 7: return mel_fixed_warp<NMELS, 7>(kt, P, lane, tcol);
-        case 8: return mel_fixed_warp<NMELS, 8>(kt, P, lane, tcol);
-        case 9: return mel_fixed_warp<NMELS, 9>(kt, P, lane, tcol);
-        case 10: return mel_fixed_warp<NMELS, 10>(kt, P, lane, tcol);
-        case 11: return mel_fixed_warp<NMELS, 11>(kt, P, lane, tcol);
-        case 12: return mel_fixed_warp<NMELS, 12>(kt, P, lane, tcol);
-        case 13: return mel_fixed_warp<NMELS, 13>(kt, P, lane, tcol);
-        case 14: return mel_fixed_warp<NMELS, 14>(kt, P, lane, tcol);
-        default: return mel_fixed_warp<NMELS, 15>(kt, P, lane, tcol);
+        default: return mel_fixed_warp<NMELS, 7>(kt, P, lane, tcol);
     }
 }
 
@@ -509,8 +561,28 @@ __device__ __forceinline__ float log10_floor(float p) {
     return fmaxf(lg2_approx(p) * kLog10_2, -10.0f);
 }
 
+// Debug timeline (-DWLM_TRACE): CTA 0 stamps clock64() at the phase boundaries of its first 48 half-tiles per warp;
+// wlm_debug_trace() copies the buffer out.  [warp][tile ordinal][event]
+#ifdef WLM_TRACE
+constexpr int kTraceTiles = 48, kTraceEvents = 12;
+__device__ unsigned long long g_trace[kWarps * kTraceTiles * kTraceEvents];
+#define WLM_TR(tn, e)                                                                              \
+    do {                                                                                           \
+        if (blockIdx.x == 0 && (tn) < kTraceTiles && lane == 0)                                    \
+            g_trace[(warp * kTraceTiles + (tn)) * kTraceEvents + (e)] = clock64();                 \
+    } while (0)
+__device__ unsigned long long g_trace_clip[kWarps * 8 * 4];      // [warp][clip seq][D, wait begin, wait end, -]
+#define WLM_TRC(seq, e)                                                                            \
+    do {                                                                                           \
+        if (blockIdx.x == 0 && (seq) < 8 && lane == 0) g_trace_clip[(warp * 8 + (seq)) * 4 + (e)] = clock64(); \
+    } while (0)
+#else
+#define WLM_TR(tn, e)
+#define WLM_TRC(seq, e)
+#endif
+
 // ================================================================================================
-// The kernel: persistent clusters of 8 CTAs, one clip per cluster at a time.
+// The kernel: persistent clusters of 6 CTAs x 2 warp groups, one clip per cluster at a time.
 // ================================================================================================
 // NMELS = 80 / 128: unrolled mel stage for the Whisper banks; NMELS = 0: table-driven mel stage.
 template <int NMELS>
@@ -518,44 +590,63 @@ __global__ void __launch_bounds__(kThreads, 1)
 logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt, const float* __restrict__ win_lane) {
     namespace cg = cooperative_groups;
     extern __shared__ __align__(128) unsigned char smem[];
-    float* raw = reinterpret_cast<float*>(smem);
-    float2* Y = reinterpret_cast<float2*>(smem + kSmemRaw);
-    float2* P = reinterpret_cast<float2*>(smem + kSmemRaw + kSmemY);
-    unsigned char* misc = smem + kSmemRaw + kSmemY + kSmemP;
-    // mbarriers (8 B each).  No CTA-wide barrier separates the stages of a tile: every hand-over between
-    // warps is one of these, so warps drift apart and FMA-bound, load-bound and idle phases overlap.
-    const uint32_t bar_raw = smem_u32(misc);         // TMA landed the tile's PCM            (tx, 1 arrival)
-    const uint32_t bar_yfull = smem_u32(misc + 8);   // all 16 warps stored stage-1 output    (16)
-    const uint32_t bar_yfree = smem_u32(misc + 16);  // all 13 stage-2 warps have read Y      (13)
-    const uint32_t bar_pfull = smem_u32(misc + 24);  // all 13 stage-2 warps stored the power (13)
-    const uint32_t bar_pfree = smem_u32(misc + 32);  // all 16 warps finished the mel stage   (16)
-    uint32_t* raw_readers = reinterpret_cast<uint32_t*>(misc + 40);   // warps done with the raw buffer
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 48);     // TMEM base address
-    float* warp_max = reinterpret_cast<float*>(misc + 64);            // [2][16] (clip parity)
-    float* cta_max = reinterpret_cast<float*>(misc + 192);            // [2] (clip parity), read by the peers
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler
+    const int grp = warp >> 3, wg = warp & 7;                 // warp group and warp inside the group
+
+    unsigned char* gbase = smem + grp * kSmemGroup;
+    float* raw = reinterpret_cast<float*>(gbase);
+    float2* Y = reinterpret_cast<float2*>(gbase + kSmemRaw);
+    float* P = reinterpret_cast<float*>(gbase + kSmemRaw + kSmemY);
+    unsigned char* misc = smem + kGroups * kSmemGroup;
+    // mbarriers (8 B each), one set per group.  No CTA- or group-wide barrier separates the stages of a
+    // tile: every hand-over between warps is one of these, so warps drift apart.
+    unsigned char* gm = misc + grp * 64;
+    const uint32_t bar_raw = smem_u32(gm);           // TMA landed the half-tile's PCM              (tx, 1 arrival)
+    const uint32_t bar_yfull = smem_u32(gm + 8);     // all 8 warps stored stage-1 output           (8)
+    const uint32_t bar_yfree = smem_u32(gm + 16);    // all 7 stage-2 warps have read Y             (7)
+    const uint32_t bar_pfull = smem_u32(gm + 24);    // all 7 stage-2 warps stored the power        (7)
+    const uint32_t bar_pfree = smem_u32(gm + 32);    // all 8 warps finished the mel stage          (8)
+    uint32_t* raw_readers = reinterpret_cast<uint32_t*>(gm + 40);     // warps done with the raw buffer
+    // clip-end max exchange (all indexed by clip parity): every virtual CTA of the cluster delivers its max into
+    // clip_max of EVERY CTA (distributed shared memory, st.async) which completes bytes on that CTA's bar_max
+    const uint32_t bar_max = smem_u32(misc + 128);                    // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 144);    // TMEM base address
+    uint32_t* grp_cnt = reinterpret_cast<uint32_t*>(misc + 160);      // [2][2] warps of the group that have contributed
+    int* grp_max = reinterpret_cast<int*>(misc + 176);                // [2][2] running max of the group (float bits, >= 0)
+    float* clip_max = reinterpret_cast<float*>(misc + 192);           // [2][12] written by the peers
 
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = static_cast<int>(cluster.block_rank());
+    const int vrank = rank * kGroups + grp;          // virtual CTA inside the clip
     const int cluster_id = blockIdx.x / kCluster;
     const int n_clusters = gridDim.x / kCluster;
 
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler
     if (tid == 0) {
-        mbar_init(bar_raw, 1);
-        mbar_init(bar_yfull, kWarps);
-        mbar_init(bar_yfree, fft::kNumSlots);
-        mbar_init(bar_pfull, fft::kNumSlots);
-        mbar_init(bar_pfree, kWarps);
-        *raw_readers = 0;
+        for (int g = 0; g < kGroups; ++g) {
+            const uint32_t b = smem_u32(misc + g * 64);
+            mbar_init(b, 1);
+            mbar_init(b + 8, kGroupWarps);
+            mbar_init(b + 16, kS2Warps);
+            mbar_init(b + 24, kS2Warps);
+            mbar_init(b + 32, kGroupWarps);
+            mbar_init(b + 48, kGroupWarps);
+            mbar_init(b + 56, kS2Warps);
+            *reinterpret_cast<uint32_t*>(misc + g * 64 + 40) = 0;
+        }
+        mbar_init(bar_max, 1);          // one arrival (this CTA's group 0, with the byte count) + 12 x 4 bytes from the peers
+        mbar_init(bar_max + 8, 1);
+        for (int i = 0; i < 4; ++i) { grp_cnt[i] = 0; grp_max[i] = 0; }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) tmem_alloc_512(smem_u32(tmem_slot));
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    cluster.sync();     // (also a CTA barrier) every peer's mbarriers exist before anyone can arrive on them remotely
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
-    // this warp's TMEM window: lane quarter (warp & 3), 96 columns at (warp >> 2) * 96
+    // the zero component of Y (imaginary part of slot 0): written once, ordered before the first stage 2 by bar_yfull
+    Y[((tid & (kGroupThreads - 1)) >> 4) * kYN1 + kPairs + (tid & 15)] = make_float2(0.f, 0.f);
+    // this warp's TMEM window: lane quarter (warp & 3), 128 columns at (warp >> 2) * 128
     const uint32_t twin = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) +
                           static_cast<uint32_t>((warp >> 2) * kTmemColsPerWarp);
 
@@ -564,192 +655,265 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
     float wv[25];
 #pragma unroll
     for (int t = 0; t < 25; ++t) wv[t] = win_lane[n1 * 25 + t];
-    const int tw = n1 == 0 ? 25 : (kNfft - 25 * n1 + 15) / 16;
+    // stage 2: slot of this half warp (warp 6's upper half repeats slot 12: same loads, same stores)
+    const int slot = min(2 * wg + (lane >> 4), fft::kNumSlots - 1);
 
-    // The CTA's work is a stream of steps, one per tile it owns (a clip in which it owns no active
-    // tile still contributes one empty step so that it takes part in that clip's cluster barrier).
-    // Program order of every warp in step i (tile t_i):
+    // The group's work is a stream of steps, one per half-tile it owns (a clip in which it owns no active
+    // half-tile still contributes one empty step so that it takes part in that clip's cluster barrier).
+    // Program order of every warp in step i (half-tile t_i):
     //   A  stage 1 of t_i            wait raw | load | last warp re-arms TMA | FFT | wait Y free | store | arrive Y full
-    //   F  output pass of the clip that ended one step ago   (cluster barrier WAIT, TMEM read-back, stores)
+    //   F  output pass of the clip that ended one step ago   (wait for the 12 maxima, TMEM read-back, stores)
     //   B  mel stage of t_{i-1}      wait P full | ... | arrive P free
-    //   D  if t_{i-1} ended a clip:  wait P free | CTA max -> cta_max | cluster barrier ARRIVE
-    //   C  stage 2 of t_i (13 warps) wait Y full | load | arrive Y free | FFT | wait P free | store | arrive P full
-    // Iteration state kept in plain scalars (a struct-per-step version spent ~100 instructions per warp and
-    // step on copies): `c*` = the step whose tile is in stage 1 / stage 2, `p*` = the previous step (mel stage).
-    auto my_tiles = [&](int n_act) { return n_act > rank ? (n_act - rank + kCluster - 1) / kCluster : 0; };
-    int cb = cluster_id, cj = 0, cn_my = 0;          // clip, step inside the clip, tiles of mine in the clip
+    //   D  if t_{i-1} ended a clip:  warp max -> group max (atomic); the last warp delivers it to all 6 CTAs
+    //   C  stage 2 of t_i (7 warps)  wait Y full | load | arrive Y free | FFT | wait P free | store | arrive P full
+    // `c*` = the step whose half-tile is in stage 1 / stage 2, `p*` = the previous step (mel stage).
+    auto my_tiles = [&](int n_act) { return n_act > vrank ? (n_act - vrank + kVCluster - 1) / kVCluster : 0; };
+    // The other group of this CTA ("partner") owns the neighbouring half-tiles vrank ^ 1 (+ 12 j).  The FFT passes of the
+    // two groups are made to ALTERNATE (A.fft1, B.fft1, A.fft2, B.fft2, A.fft1, ...) by waiting on the partner's barriers,
+    // so that the FMA-bound FFT of one group always runs over the shared-memory-bound loads / stores / mel pass of the
+    // other (left alone, the groups settle with their FFTs on top of each other: measured with -DWLM_TRACE).
+    // `otn0` = ordinal, among the partner's half-tiles, of its first one in the current clip; `opn` = how many it has there.
+    const int ovrank = vrank ^ 1;
+    auto partner_tiles = [&](int n_act) { return n_act > ovrank ? (n_act - ovrank + kVCluster - 1) / kVCluster : 0; };
+    const uint32_t bar_f1 = smem_u32(gm + 48), bar_f2 = smem_u32(gm + 56);      // this group's FFT 1 / FFT 2 arithmetic is done (8 / 7)
+    const uint32_t obar_f1 = smem_u32(misc + (grp ^ 1) * 64 + 48), obar_f2 = smem_u32(misc + (grp ^ 1) * 64 + 56);
+    int otn0 = 0, opn = 0;
+    int cb = cluster_id, cj = 0, cn_my = 0;          // clip, step inside the clip, half-tiles of mine in the clip
     bool cvalid = cb < a.B;
     ClipCtx cc;
     cc.b = cb; cc.len = 0; cc.n_act = 0; cc.base = 0;
     if (cvalid) {
         cc = clip_ctx(a, cb);
         cn_my = my_tiles(cc.n_act);
+        opn = partner_tiles(cc.n_act);
     }
     bool pvalid = false, phas = false, plast = false;
     int pb = 0, pj = 0, ptile = 0, pn_my = 0;
-    // TMA target after tile (clip cb0, step j0): the next tile of the same clip, else the first tile of the
-    // next clip in which this CTA owns one.  Executed by ONE lane (the last warp to finish reading raw).
+    // TMA target after (clip cb0, step j0): the next half-tile of the same clip, else the first half-tile of
+    // the next clip in which this group owns one.  Executed by ONE lane (the last warp to finish reading raw).
     auto issue_next_tile = [&](int cb0, const ClipCtx& c0, int n_my0, int j0) {
         if (j0 + 1 < n_my0) {
-            tile_issue_tma(a, c0, rank + (j0 + 1) * kCluster, raw, bar_raw);
+            tile_issue_tma(a, c0, vrank + (j0 + 1) * kVCluster, raw, bar_raw);
             return;
         }
         for (int nb = cb0 + n_clusters; nb < a.B; nb += n_clusters) {
             const ClipCtx c2 = clip_ctx(a, nb);
-            if (c2.n_act > rank) {
-                tile_issue_tma(a, c2, rank, raw, bar_raw);
+            if (c2.n_act > vrank) {
+                tile_issue_tma(a, c2, vrank, raw, bar_raw);
                 return;
             }
         }
     };
 
-    // Phase bookkeeping: the n-th tile this CTA processes (n = 0, 1, ...) uses phase n of every barrier,
+    // Phase bookkeeping: the n-th half-tile this group processes (n = 0, 1, ...) uses phase n of every barrier,
     // i.e. parity n & 1.  A wait for phase n is only issued by a warp that has already arrived on phase n
     // or whose own later work is needed to complete phase n+1, so the barrier is never more than one
     // phase ahead of a waiter.
-    int fin_parity = 0;                      // parity of the clip whose max is exchanged next
-    int tnum = 0, prev_tnum = 0;             // ordinal of cur's / prev's tile among the tiles of this CTA
-    if (tid == 0 && cvalid) {
-        if (cn_my > 0) tile_issue_tma(a, cc, rank, raw, bar_raw);
+    int fin_seq = 0;                         // clips whose output pass this warp has done; parity = slot of the exchange
+    int tnum = 0, prev_tnum = 0;             // ordinal of cur's / prev's half-tile among those of this group
+    if ((tid & (kGroupThreads - 1)) == 0 && cvalid) {
+        if (cn_my > 0) tile_issue_tma(a, cc, vrank, raw, bar_raw);
         else issue_next_tile(cb, cc, 0, 0);
     }
-    float2 mx = make_float2(0.f, 0.f);       // running max of the mel power of the clip in flight (>= 0)
-    bool pend = false;                       // an output pass is owed (cluster barrier arrived, not yet waited)
+    float mx = 0.f;                          // running max of the mel power of the clip in flight (>= 0)
+    bool pend = false;                       // an output pass is owed (max delivered, not yet waited for)
     int pend_b = 0, pend_n_my = 0;
+    int out_j = 0;                           // next retained half-tile of the pending clip to write out
+    bool have_max = false;                   // the pending clip's max has arrived (floor_v valid)
+    float floor_v = 0.f;
 
     while (cvalid || pvalid || pend) {
         const bool do_tile = cvalid && cj < cn_my;
-        const int ctile = rank + cj * kCluster;
+        const int ctile = vrank + cj * kVCluster;
         // ---- A: stage 1 ----------------------------------------------------------------------------
         if (do_tile) {
+            WLM_TR(tnum, 0);
             mbar_wait(bar_raw, tnum & 1);
-            tile_fixup(a, cc, ctile, raw);
-            stage1(raw, Y, wv, tw, warp, lane,
-                   [&]() {   // this warp is done with raw: the last of the 16 re-arms the TMA for the next tile
+            WLM_TR(tnum, 1);
+            tile_fixup(a, cc, ctile, raw, grp, tid & (kGroupThreads - 1));
+            stage1(raw, Y, wv, wg, lane,
+                   [&]() {   // this warp is done with raw: the last of the 8 re-arms the TMA for the next half-tile
                        __syncwarp();
                        if (lane == 0) {
                            __threadfence_block();
                            const uint32_t old = atomicAdd(raw_readers, 1u);
-                           if (old == kWarps - 1) {
+                           if (old == kGroupWarps - 1) {
                                *raw_readers = 0;
                                __threadfence_block();
                                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                                issue_next_tile(cb, cc, cn_my, cj);
                            }
                        }
-                   },
-                   [&]() {   // stage 2 of the previous tile must have read Y
+                       // stage 2 of the previous half-tile must have read Y (long done: waiting here, before the
+                       // FFT, lets the stores below interleave with its tail)
+                       WLM_TR(tnum, 2);
                        if (tnum > 0) mbar_wait(bar_yfree, (tnum - 1) & 1);
+#ifdef WLM_ALTERNATE
+                       // FFT turn-taking: B.fft1(j) after A.fft1(j); A.fft1(j) after B.fft2(j-1)
+                       if (grp == 1) {
+                           if (cj < opn) mbar_wait(obar_f1, (otn0 + cj) & 1);
+                       } else if (cj > 0 && cj - 1 < opn) {
+                           mbar_wait(obar_f2, (otn0 + cj - 1) & 1);
+                       }
+#endif
+                       WLM_TR(tnum, 3);
+                   },
+                   [&]() {
+                       WLM_TR(tnum, 4);
+#ifdef WLM_ALTERNATE
+                       __syncwarp();
+                       if (lane == 0) mbar_arrive(bar_f1);
+#endif
                    });
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_yfull);
+            WLM_TR(tnum, 5);
         }
-        // ---- F: output pass of the clip that ended one step ago -----------------------------------------
-        if (pend) {
-            asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-            float pmax = 0.f;
-            if (lane < kCluster) pmax = *cluster.map_shared_rank(cta_max + fin_parity, lane);
-#pragma unroll
-            for (int o = 4; o > 0; o >>= 1) pmax = fmaxf(pmax, __shfl_xor_sync(0xffffffffu, pmax, o));
-            pmax = __shfl_sync(0xffffffffu, pmax, 0);
-            fin_parity ^= 1;
-            const float gmax = log10_floor(pmax);                 // TF-FE:157
-            const float floor_v = fmaxf(gmax - 8.0f, -10.0f);     // TF-FE:158 (log-mel is never below -10)
-            if (rank == 0 && tid == 0 && a.gmax) a.gmax[pend_b] = gmax;
-
-            // single pass: TMEM -> (max(log10, gmax-8)+4)/4 -> HBM
-            tmem_wait_st();
+        // ---- F: output of the clip that ended one step ago, ONE retained half-tile per step ----------------------
+        // (the slot the mel stage below is about to overwrite: tcgen05.ld is 64 B/clk per SM, so a whole-clip pass by
+        // all 16 warps at once stalls everything for ~4k cycles; spread over the next clip's steps it hides under the FFTs)
+        auto output_slot = [&](int j) {
             constexpr float kLog10_2 = 0.30102999566398120f;
-            const int nf = kt.nf[warp];
-            float* ob = a.out + (static_cast<int64_t>(pend_b) * a.n_mels + kt.m0[warp]) * kNFrames + pair_frame_a(lane);
-            for (int j = 0; j < pend_n_my; ++j) {
-                float r[16];
-                tmem_ld_x16(twin + j * kTmemColsPerTile, r);
-                const int f0 = (rank + j * kCluster) * kTile;
-                const int fa = f0 + pair_frame_a(lane);
-                float* of = ob + f0;
-                const bool va = fa < kNFrames;      // 3000 is even: both frames of the pair or none
-#define WLM_OUT_ROW(q)                                                                                         \
-    case (q) + 1: {                                                                                            \
-        float2 lg = __fmul2_rn(make_float2(lg2_approx(r[2 * (q)]), lg2_approx(r[2 * (q) + 1])),                \
-                               make_float2(kLog10_2, kLog10_2));                                               \
-        lg.x = fmaxf(lg.x, floor_v);                                                                           \
-        lg.y = fmaxf(lg.y, floor_v);                                                                           \
-        lg = __ffma2_rn(lg, make_float2(0.25f, 0.25f), make_float2(1.0f, 1.0f)); /* (x+4)/4, TF-FE:161 */       \
-        if (va) *reinterpret_cast<float2*>(of + (q) * kNFrames) = lg;                                          \
-    }
-                switch (nf) {   // fall-through: exactly nf rows, static register indices
-                    WLM_OUT_ROW(7) WLM_OUT_ROW(6) WLM_OUT_ROW(5) WLM_OUT_ROW(4)
-                    WLM_OUT_ROW(3) WLM_OUT_ROW(2) WLM_OUT_ROW(1) WLM_OUT_ROW(0)
-                    default: break;
+            const int nf = kt.nf[wg];
+            float r[16];
+            tmem_wait_st();
+            tmem_ld_x16(twin + j * kTmemColsPerTile, r);
+            const int f0 = (vrank + j * kVCluster) * kTile;
+            float* of = a.out + (static_cast<int64_t>(pend_b) * a.n_mels + kt.m0[wg]) * kNFrames + lane + f0;
+            const bool va = f0 + lane < kNFrames;
+            // rows in blocks of four: straight-line code inside a block, so four MUFU.LG2 chains overlap
+#pragma unroll
+            for (int q0 = 0; q0 < kMaxFiltersPerWarp; q0 += 4) {
+                if (q0 < nf) {
+                    float lg[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        lg[i] = fmaxf(lg2_approx(r[q0 + i]) * kLog10_2, floor_v);
+                        lg[i] = fmaf(lg[i], 0.25f, 1.0f);   // (x+4)/4, TF-FE:161
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (va && q0 + i < nf) of[(q0 + i) * kNFrames] = lg[i];
                 }
-#undef WLM_OUT_ROW
             }
-            // tiles of mine that hold no real sample: log-mel is exactly -10 everywhere
-            const float silent = (floor_v + 4.0f) * 0.25f;
-            for (int tile = rank + pend_n_my * kCluster; tile < kTilesPerClip; tile += kCluster) {
-                const int fa = tile * kTile + pair_frame_a(lane);
-                float* of = ob + tile * kTile;
-                if (fa < kNFrames)
-                    for (int q = 0; q < nf; ++q) *reinterpret_cast<float2*>(of + q * kNFrames) = make_float2(silent, silent);
+        };
+        if (pend) {
+            if (!have_max) {    // first step after the clip ended: the 12 maxima
+                const int fpar = fin_seq & 1;
+                WLM_TRC(fin_seq, 1);
+                mbar_wait_cluster(bar_max + fpar * 8, (fin_seq >> 1) & 1);
+                WLM_TRC(fin_seq, 2);
+                float pmax = lane < kVCluster ? clip_max[fpar * kVCluster + lane] : 0.f;
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) pmax = fmaxf(pmax, __shfl_xor_sync(0xffffffffu, pmax, o));
+                pmax = __shfl_sync(0xffffffffu, pmax, 0);
+                ++fin_seq;
+                have_max = true;
+                const float gmax = log10_floor(pmax);                 // TF-FE:157
+                floor_v = fmaxf(gmax - 8.0f, -10.0f);                 // TF-FE:158 (log-mel is never below -10)
+                if (vrank == 0 && (tid & (kGroupThreads - 1)) == 0 && a.gmax) a.gmax[pend_b] = gmax;
+                // half-tiles of mine that hold no real sample: log-mel is exactly -10 everywhere
+                const float silent = (floor_v + 4.0f) * 0.25f;
+                const int nf = kt.nf[wg];
+                float* ob = a.out + (static_cast<int64_t>(pend_b) * a.n_mels + kt.m0[wg]) * kNFrames + lane;
+                for (int tile = vrank + pend_n_my * kVCluster; tile < kTilesPerClip; tile += kVCluster) {
+                    float* of = ob + tile * kTile;
+                    if (tile * kTile + lane < kNFrames)
+                        for (int q = 0; q < nf; ++q) of[q * kNFrames] = silent;
+                }
             }
-            pend = false;
+            if (out_j < pend_n_my) output_slot(out_j++);
+            if (out_j >= pend_n_my) pend = false;
         }
-        // ---- B: mel stage of the previous tile -------------------------------------------------------------
+        // ---- B: mel stage of the previous half-tile ---------------------------------------------------------
         const bool clip_ends = pvalid && plast;
         const bool mel_tile = pvalid && phas;
-        const int cpar = fin_parity;             // F has run: this is the parity of the clip ending now
+        const int cpar = fin_seq & 1;            // F has run: this is the parity of the clip ending now
+        float wmax = 0.f;                        // this warp's max over the clip (valid when clip_ends)
         if (mel_tile) {
+            WLM_TR(prev_tnum, 10);
             mbar_wait(bar_pfull, prev_tnum & 1);
             const uint32_t tcol = twin + pj * kTmemColsPerTile;
-            const float2 m2 = NMELS == 0 ? mel_stage(kt, P, warp, lane, tcol) : mel_fixed<NMELS == 0 ? 80 : NMELS>(kt, P, warp, lane, tcol);
-            if (ptile * kTile + pair_frame_a(lane) < kNFrames) {     // frames past 3000 do not exist
-                mx.x = fmaxf(mx.x, m2.x);
-                mx.y = fmaxf(mx.y, m2.y);
-            }
+#ifdef WLM_KO_MEL
+            const float m1 = P[lane] + static_cast<float>(tcol & 1);
+#else
+            const float m1 = NMELS == 0 ? mel_stage(kt, P, wg, lane, tcol) : mel_fixed<NMELS == 0 ? 80 : NMELS>(kt, P, wg, lane, tcol);
+#endif
+            if (ptile * kTile + lane < kNFrames) mx = fmaxf(mx, m1);     // frames past 3000 do not exist
             if (clip_ends) {
-                float v = fmaxf(mx.x, mx.y);
+                wmax = mx;
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-                if (lane == 0) warp_max[cpar * kWarps + warp] = v;
-                mx = make_float2(0.f, 0.f);
+                for (int o = 16; o > 0; o >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+                mx = 0.f;
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_pfree);   // phase prev_tnum
+            WLM_TR(prev_tnum, 11);
         }
-        // ---- D: the clip ended: CTA max -> cta_max (every warp writes the same value), cluster ARRIVE ---------
-        // Done before stage 2 so that the peers get a whole step of slack before anyone WAITs (F, next step).
+        // ---- D: the clip ended: warp max -> group max; the LAST warp of the group to get here delivers the group's
+        // max to all 6 CTAs (remote store + remote mbarrier arrive).  Nobody waits; the peers get a whole step of
+        // slack before anyone needs the result (F, next step).
         if (clip_ends) {
-            if (mel_tile) mbar_wait(bar_pfree, prev_tnum & 1);   // every warp's warp_max is visible
-            float c = (mel_tile && lane < kWarps) ? warp_max[cpar * kWarps + lane] : 0.f;
-#pragma unroll
-            for (int o = 8; o > 0; o >>= 1) c = fmaxf(c, __shfl_xor_sync(0xffffffffu, c, o));
-            if (lane == 0) cta_max[cpar] = c;
-            asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+            while (pend) {      // (only when this clip had fewer half-tiles than the one before it: finish that one first)
+                if (out_j < pend_n_my) output_slot(out_j++);
+                if (out_j >= pend_n_my) pend = false;
+            }
+            WLM_TRC(fin_seq, 0);
+            if (lane == 0) {
+                int* gmx = grp_max + cpar * kGroups + grp;
+                uint32_t* gct = grp_cnt + cpar * kGroups + grp;
+                if (mel_tile) atomicMax(gmx, __float_as_int(wmax));     // non-negative floats order like their bit patterns
+                __threadfence_block();
+                if (atomicAdd(gct, 1u) == kGroupWarps - 1) {
+                    __threadfence_block();
+                    const float m = __int_as_float(atomicExch(gmx, 0));  // (reset for the clip after next)
+                    atomicExch(gct, 0u);
+                    // Fire-and-forget: st.async writes the value into the peer's clip_max and completes 4 bytes on the
+                    // peer's bar_max (a remote store + release-arrive pair cost ~900 cycles EACH on the one warp the
+                    // whole group was then waiting for).  Every CTA's group 0 posts the expectation of 12 x 4 bytes.
+                    const uint32_t slot_l = smem_u32(clip_max + cpar * kVCluster + vrank), bar_l = bar_max + cpar * 8;
+                    if (grp == 0) mbar_expect_tx(bar_l, 4u * kVCluster);
+                    for (int r = 0; r < kCluster; ++r) {
+                        uint32_t slot_r, bar_r;
+                        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(slot_r) : "r"(slot_l), "r"(r));
+                        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(bar_r) : "r"(bar_l), "r"(r));
+                        asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
+                                     ::"r"(slot_r), "r"(__float_as_uint(m)), "r"(bar_r) : "memory");
+                    }
+                }
+            }
             pend = true;
+            have_max = false;
+            out_j = 0;
             pend_b = pb;
             pend_n_my = pn_my;
         }
         // ---- C: stage 2 ----------------------------------------------------------------------------------
-        // 13 slots on 16 warps: one scheduler gets 4 tasks, the others 3.  Rotating the assignment by one
-        // warp per tile moves the extra task around, so over four tiles every scheduler issues the same work.
-#ifdef WLM_OPT_ROT
-        const int slot = (warp + tnum) & 15;
-#else
-        const int slot = warp;
-#endif
-        if (do_tile && slot < fft::kNumSlots) {
+        if (do_tile && wg < kS2Warps) {
+            WLM_TR(tnum, 6);
             mbar_wait(bar_yfull, tnum & 1);
-            stage2(kt, Y, P, slot, lane,
+            WLM_TR(tnum, 7);
+            stage2(Y, P, slot, lane & 15,
                    [&]() {
                        __syncwarp();
                        if (lane == 0) mbar_arrive(bar_yfree);   // phase tnum
-                   },
-                   [&]() {   // the mel stage of the previous tile must have read P (all 16 warps)
+                       // the mel stage of the previous half-tile must have read P (all 8 warps)
                        if (tnum > 0) mbar_wait(bar_pfree, (tnum - 1) & 1);
+#ifdef WLM_ALTERNATE
+                       // FFT turn-taking: A.fft2(j) after B.fft1(j); B.fft2(j) after A.fft2(j)
+                       if (cj < opn) mbar_wait(grp == 0 ? obar_f1 : obar_f2, (otn0 + cj) & 1);
+#endif
+                       WLM_TR(tnum, 8);
+                   },
+                   [&]() {
+#ifdef WLM_ALTERNATE
+                       __syncwarp();
+                       if (lane == 0) mbar_arrive(bar_f2);
+#endif
                    });
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_pfull);   // phase tnum
+            WLM_TR(tnum, 9);
         }
         // this step becomes the previous one; advance to the next step of the stream
         const int steps = cn_my > 0 ? cn_my : 1;
@@ -764,17 +928,20 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
                 cb += n_clusters;
                 cj = 0;
                 cn_my = 0;
+                otn0 += opn;
+                opn = 0;
                 cvalid = cb < a.B;
                 if (cvalid) {
                     cc = clip_ctx(a, cb);
                     cn_my = my_tiles(cc.n_act);
+                    opn = partner_tiles(cc.n_act);
                 }
             }
         }
     }
     // all TMEM reads are complete (tcgen05.wait::ld inside tmem_ld_x16); release the allocation
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    cluster.sync();   // also keeps every CTA's shared memory alive until its peers have read cta_max
+    cluster.sync();   // also keeps every CTA's shared memory alive until its peers have delivered their last max
     if (warp == 0) tmem_dealloc_512(tmem_base);
 }
 

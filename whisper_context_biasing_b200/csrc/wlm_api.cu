@@ -504,3 +504,19 @@ extern "C" int wlm_logmel_host(wlm_plan* p, const void* const* clips_host, const
     WLM_CUDA(cudaStreamSynchronize(p->copy_stream));
     return WLM_OK;
 }
+
+#if defined(WLM_TRACE) && defined(WLM_HAVE_FUSED)
+// debug builds only: copy the phase timeline of CTA 0 out of the device (see logmel_fused.cuh)
+extern "C" int wlm_debug_trace(unsigned long long* dst, size_t count) {
+    const size_t n = sizeof(fused::g_trace) / sizeof(unsigned long long);
+    if (count < n) return (int)n;
+    WLM_CUDA(cudaMemcpyFromSymbol(dst, fused::g_trace, sizeof(fused::g_trace)));
+    return (int)n;
+}
+extern "C" int wlm_debug_trace_clip(unsigned long long* dst, size_t count) {
+    const size_t n = sizeof(fused::g_trace_clip) / sizeof(unsigned long long);
+    if (count < n) return (int)n;
+    WLM_CUDA(cudaMemcpyFromSymbol(dst, fused::g_trace_clip, sizeof(fused::g_trace_clip)));
+    return (int)n;
+}
+#endif
