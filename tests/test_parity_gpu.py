@@ -113,6 +113,32 @@ def test_ragged_and_edge_lengths(fe):
     assert np.all(got[0] == -1.5)
 
 
+
+def test_long_ragged_stream(fe):
+    """More clips than co-resident clusters, lengths all over the place (empty, sub-frame, around every half-tile and
+    sub-region boundary, full, over-long): every cluster then walks a STREAM of clips whose number of active half-tiles
+    changes from clip to clip -- the clip-end bookkeeping (max exchange parity, retained half-tiles of a longer clip
+    still owed when a shorter one ends, empty steps).  Gate: bit-identical to each clip extracted alone, plus spot
+    parity against the oracle."""
+    import torch
+
+    rng = np.random.default_rng(11)
+    special = [0, 1, 200, 4919, 4920, 4921, 5119, 5120, 5121, 2359, 2360, 2361, 10040, 61240, 61241, 479999, 480000, 500000]
+    lengths = special + [int(x) for x in rng.integers(0, 480001, size=70)] + [int(x) for x in rng.integers(0, 30000, size=40)]
+    rng.shuffle(lengths)
+    clips = [O.synth_clip(O.FAMILIES[i % len(O.FAMILIES)], L, 1000 + i) for i, L in enumerate(lengths)]
+    for m in (80, 128):
+        ex = fe[m]
+        assert len(clips) > 4 * ex.max_clusters
+        got = ex(clips, sampling_rate=16000, return_tensors="pt").input_features
+        for i in list(range(0, len(clips), 7)) + [lengths.index(L) for L in special]:
+            one = ex(clips[i], sampling_rate=16000, return_tensors="pt").input_features
+            assert torch.equal(one[0], got[i]), (m, i, lengths[i])
+        idx = [lengths.index(0), lengths.index(5121), lengths.index(480000), 3, 50]
+        ref = O.extract([clips[i] for i in idx], m, "f64")
+        assert np.abs(got[idx].cpu().numpy() - ref).max() <= TOL
+
+
 def test_known_answers(fe):
     z = fe[80]([np.zeros(48000, np.float32), O.synth_clip("tiny", 48000, 1)], sampling_rate=16000,
                return_tensors="np").input_features

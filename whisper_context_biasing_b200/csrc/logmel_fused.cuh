@@ -630,8 +630,6 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
             mbar_init(b + 16, kS2Warps);
             mbar_init(b + 24, kS2Warps);
             mbar_init(b + 32, kGroupWarps);
-            mbar_init(b + 48, kGroupWarps);
-            mbar_init(b + 56, kS2Warps);
             *reinterpret_cast<uint32_t*>(misc + g * 64 + 40) = 0;
         }
         mbar_init(bar_max, 1);          // one arrival (this CTA's group 0, with the byte count) + 12 x 4 bytes from the peers
@@ -668,16 +666,6 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
     //   C  stage 2 of t_i (7 warps)  wait Y full | load | arrive Y free | FFT | wait P free | store | arrive P full
     // `c*` = the step whose half-tile is in stage 1 / stage 2, `p*` = the previous step (mel stage).
     auto my_tiles = [&](int n_act) { return n_act > vrank ? (n_act - vrank + kVCluster - 1) / kVCluster : 0; };
-    // The other group of this CTA ("partner") owns the neighbouring half-tiles vrank ^ 1 (+ 12 j).  The FFT passes of the
-    // two groups are made to ALTERNATE (A.fft1, B.fft1, A.fft2, B.fft2, A.fft1, ...) by waiting on the partner's barriers,
-    // so that the FMA-bound FFT of one group always runs over the shared-memory-bound loads / stores / mel pass of the
-    // other (left alone, the groups settle with their FFTs on top of each other: measured with -DWLM_TRACE).
-    // `otn0` = ordinal, among the partner's half-tiles, of its first one in the current clip; `opn` = how many it has there.
-    const int ovrank = vrank ^ 1;
-    auto partner_tiles = [&](int n_act) { return n_act > ovrank ? (n_act - ovrank + kVCluster - 1) / kVCluster : 0; };
-    const uint32_t bar_f1 = smem_u32(gm + 48), bar_f2 = smem_u32(gm + 56);      // this group's FFT 1 / FFT 2 arithmetic is done (8 / 7)
-    const uint32_t obar_f1 = smem_u32(misc + (grp ^ 1) * 64 + 48), obar_f2 = smem_u32(misc + (grp ^ 1) * 64 + 56);
-    int otn0 = 0, opn = 0;
     int cb = cluster_id, cj = 0, cn_my = 0;          // clip, step inside the clip, half-tiles of mine in the clip
     bool cvalid = cb < a.B;
     ClipCtx cc;
@@ -685,7 +673,6 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
     if (cvalid) {
         cc = clip_ctx(a, cb);
         cn_my = my_tiles(cc.n_act);
-        opn = partner_tiles(cc.n_act);
     }
     bool pvalid = false, phas = false, plast = false;
     int pb = 0, pj = 0, ptile = 0, pn_my = 0;
@@ -748,22 +735,10 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
                        // FFT, lets the stores below interleave with its tail)
                        WLM_TR(tnum, 2);
                        if (tnum > 0) mbar_wait(bar_yfree, (tnum - 1) & 1);
-#ifdef WLM_ALTERNATE
-                       // FFT turn-taking: B.fft1(j) after A.fft1(j); A.fft1(j) after B.fft2(j-1)
-                       if (grp == 1) {
-                           if (cj < opn) mbar_wait(obar_f1, (otn0 + cj) & 1);
-                       } else if (cj > 0 && cj - 1 < opn) {
-                           mbar_wait(obar_f2, (otn0 + cj - 1) & 1);
-                       }
-#endif
                        WLM_TR(tnum, 3);
                    },
                    [&]() {
                        WLM_TR(tnum, 4);
-#ifdef WLM_ALTERNATE
-                       __syncwarp();
-                       if (lane == 0) mbar_arrive(bar_f1);
-#endif
                    });
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_yfull);
@@ -899,17 +874,9 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
                        if (lane == 0) mbar_arrive(bar_yfree);   // phase tnum
                        // the mel stage of the previous half-tile must have read P (all 8 warps)
                        if (tnum > 0) mbar_wait(bar_pfree, (tnum - 1) & 1);
-#ifdef WLM_ALTERNATE
-                       // FFT turn-taking: A.fft2(j) after B.fft1(j); B.fft2(j) after A.fft2(j)
-                       if (cj < opn) mbar_wait(grp == 0 ? obar_f1 : obar_f2, (otn0 + cj) & 1);
-#endif
                        WLM_TR(tnum, 8);
                    },
                    [&]() {
-#ifdef WLM_ALTERNATE
-                       __syncwarp();
-                       if (lane == 0) mbar_arrive(bar_f2);
-#endif
                    });
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_pfull);   // phase tnum
@@ -928,13 +895,10 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
                 cb += n_clusters;
                 cj = 0;
                 cn_my = 0;
-                otn0 += opn;
-                opn = 0;
                 cvalid = cb < a.B;
                 if (cvalid) {
                     cc = clip_ctx(a, cb);
                     cn_my = my_tiles(cc.n_act);
-                    opn = partner_tiles(cc.n_act);
                 }
             }
         }
