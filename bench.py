@@ -183,13 +183,16 @@ def run_ours(args, wl, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     dist = None
+    json_fd = None
     if world > 1:
         import torch.distributed as dist_mod
 
         dist = dist_mod
-        # NCCL prints "NCCL version ..." to stdout at VERSION level; keep stdout to the one JSON line
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # NCCL writes "NCCL version ..." straight to file descriptor 1 (at any NCCL_DEBUG level): point fd 1 at stderr for
+        # the duration of the run and keep the real stdout for the ONE JSON line
+        sys.stdout.flush()
+        json_fd = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group(backend="nccl", device_id=dev)
 
     from whisper_context_biasing_b200.sharding import clip_shard
@@ -356,19 +359,38 @@ def run_ours(args, wl, rank, world, local_rank):
                          "launch_ms": launch_ms},
             "clocks": clocks,
         }
+        if n_mels in ALGORITHMIC_MFLOP_PER_CLIP and not variable:
+            sm_mhz = float((clocks or {}).get("sm_max_mhz") or 1965.0)
+            fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+            fp32_ach = ALGORITHMIC_MFLOP_PER_CLIP[n_mels] * 1e6 * B / (launch_ms * 1e-3) / 1e12
+            line["roofline_fp32"] = {"bound": "fp32-cuda-core", "achieved": fp32_ach, "peak": fp32_peak, "unit": "TFLOP/s",
+                                     "frac": fp32_ach / fp32_peak, "peak_source": "nominal: 148 SMs x 128 lanes x 2 x max SM clock",
+                                     "ncu_pct_of_peak_while_active": NCU_PIPE_PCT[n_mels],
+                                     "note": "the FFT is add-heavy (FADD2 = one issue, two lanes, no multiply): the FMA-pipe "
+                                             "counter, not the flop fraction, says how busy the CUDA cores are"}
         if not args.no_cpu_baseline and world >= 1:
             line["cpu_baseline"] = cpu_baseline(n_mels)
-        print(json.dumps(line), flush=True)
+        if json_fd is not None:
+            os.write(json_fd, (json.dumps(line) + "\n").encode())
+        else:
+            print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of the fused kernel per clip, from the `ncu --set full`
-# captures summarised under profiles/ (r01_c2_80mel_summary.txt: 491.59 + 208.66 MB for 256 clips;
-# r01_c3_128mel_summary.txt: 1966.18 + 1522.33 MB for 1024 clips).  Algorithmic: 2.88 / 3.456 MB per clip;
+# captures summarised under profiles/ (r01b_c2_80mel_summary.txt: 491.76 + 203.92 MB for 256 clips;
+# r01b_c3_128mel_summary.txt: 1966.15 + 1521.01 MB for 1024 clips).  Algorithmic: 2.88 / 3.456 MB per clip;
 # the measured traffic is slightly lower because the tail of the output is still dirty in L2 at kernel end.
-KERNEL_DRAM_TRAFFIC_PER_CLIP = {80: 700240384 / 256, 128: 3488505000 / 1024}
+KERNEL_DRAM_TRAFFIC_PER_CLIP = {80: 695678208 / 256, 128: 3487154000 / 1024}
+
+# FP32 side of the roofline (SURVEY 8d convention: 32.49 / 33.23 MFLOP per 30 s clip; nominal CUDA-core peak =
+# 148 SMs x 128 lanes x 2 flop x SM clock).  The pipe utilisations are the ncu counters of the same captures
+# (sm__pipe_fma_cycles_active, l1tex__data_pipe_lsu_wavefronts_mem_shared, smsp__issue_active: % of peak while active).
+ALGORITHMIC_MFLOP_PER_CLIP = {80: 32.49, 128: 33.23}
+NCU_PIPE_PCT = {80: {"fma_pipe": 48.5, "shared_memory_wavefronts": 44.9, "issue_slots": 59.8},
+                128: {"fma_pipe": 47.8, "shared_memory_wavefronts": 44.6, "issue_slots": 60.4}}
 
 
 def cpu_baseline(n_mels):
