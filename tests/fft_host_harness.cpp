@@ -37,3 +37,9 @@ extern "C" void pfa_rfft400(const double* x, double* re, double* im) {
     }
 }
 extern "C" int pfa_output_bin(int k1, int k2) { return output_bin(k1, k2); }
+
+// the kernel's P layout: stage 2 leaves |X|^2 of (slot, FFT16 output position) in row 16 slot + position,
+// the mel stage reads bin k from row_of_bin(k)
+extern "C" int pfa_row_of_bin(int k) { return row_of_bin(k); }
+extern "C" int pfa_bin_of_row(int row) { return output_bin(fft16_k1_of_pos(row & 15), kSlotK2[row >> 4]); }
+extern "C" int pfa_fft16_pos_of_k1(int k1) { return fft16_slot_of_k1(k1); }

@@ -50,3 +50,17 @@ def test_every_bin_exactly_once(harness):
             seen.setdefault(harness.pfa_output_bin(k1, k2), []).append((k1, k2))
     assert sorted(seen) == list(range(201))
     assert all(len(v) == 1 for v in seen.values())
+
+
+def test_power_row_map_is_the_inverse_of_the_stage2_layout(harness):
+    """Stage 2 writes |X|^2 of (slot, FFT16 output position i) to row 16*slot + i; the mel stage reads FFT bin k from
+    row_of_bin(k).  Every bin must map to a row that holds exactly that bin, and position <-> k1 must be a bijection."""
+    for f in (harness.pfa_row_of_bin, harness.pfa_bin_of_row, harness.pfa_fft16_pos_of_k1):
+        f.restype = C.c_int
+    rows = [harness.pfa_row_of_bin(k) for k in range(201)]
+    assert all(0 <= r < 13 * 16 for r in rows) and len(set(rows)) == 201
+    assert all(harness.pfa_bin_of_row(r) == k for k, r in enumerate(rows))
+    assert sorted(harness.pfa_fft16_pos_of_k1(k1) for k1 in range(16)) == list(range(16))
+    # every row of every slot holds a bin in range (slot 0 holds seven of its bins twice: k1 and 16 - k1)
+    bins = [harness.pfa_bin_of_row(r) for r in range(13 * 16)]
+    assert min(bins) == 0 and max(bins) == 200 and len(set(bins)) == 201
