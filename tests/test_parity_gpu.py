@@ -336,3 +336,32 @@ def test_collator_step_c5(fe):
     pre = [{"input_features": feats[i], "labels": items[i]["labels"], "bias_spans": items[i]["bias_spans"]} for i in range(3)]
     b2 = coll(pre)
     assert torch.equal(b2["input_features"], feats[:3])
+
+
+def test_feature_cache_over_the_extractor(fe):
+    """second epoch = pure hits, bit-identical features, no new kernel launches and no loader calls."""
+    import torch
+
+    from whisper_context_biasing_b200 import FeatureCache
+
+    ex = fe[80]
+    clips = {k: O.synth_clip("speech", 30000 + 1000 * k, 300 + k) for k in range(12)}
+    loads = []
+
+    def load(k):
+        loads.append(k)
+        return clips[k]
+
+    cache = FeatureCache(ex, capacity_bytes=16 * 80 * 3000 * 4)
+    order = [3, 1, 4, 1, 5, 9, 2, 6]
+    first = cache.get_many(order, load)
+    assert first.is_cuda and tuple(first.shape) == (8, 80, 3000)
+    direct = ex([clips[k] for k in order], sampling_rate=16000, return_tensors="pt").input_features
+    assert torch.equal(first, direct)
+    n_launch, n_load = ex.launch_count, len(loads)
+    again = cache.get_many(order[::-1], load)
+    assert torch.equal(again, direct.flip(0))
+    assert ex.launch_count == n_launch and len(loads) == n_load
+    half = FeatureCache(ex, capacity_bytes=16 * 80 * 3000 * 2, dtype=torch.float16)
+    h = half.get_many(order, load)
+    assert (h - direct).abs().max().item() <= 1e-3          # fp16 storage of values in [-1.5, 1.5]
