@@ -71,19 +71,22 @@ constexpr int kTileSamples = (kTile - 1) * kHop + kNfft;       // 5360
 static_assert(kSubLen % 32 == 16, "the two sub-regions must sit 16 banks apart");
 static_assert(kSubStep + kSubLen == kTileSamples, "sub-regions cover the half-tile");
 
-// Y (stage 1 -> stage 2), per group: [n1][26 components][16 pairs] float2 (two frames); slot s reads components
-// 2 s (Re) and 2 s + 1 (Im): component 0 = Re Y[k2=0], component 1 = zeros (written once, slot 0 is purely real).
-// (A [n1][pair][component] layout with 128-bit accesses was measured: ptxas assembles every STS.128 with four MOVs.)
-constexpr int kYComps = 2 * fft::kNumSlots;                    // 26
-constexpr int kYN1 = kYComps * kPairs + 1;                     // 417 float2 per n1 row (odd: 16 lanes x 8 B conflict-free)
-constexpr int kYFloat2 = 16 * kYN1;
-// P (stage 2 -> mel), per group: [row = slot * 16 + position in the FFT16 output][32 frames] float
-constexpr int kPRows = fft::kNumSlots * 16;                    // 208 (201 distinct bins; slot 0 holds each of its bins twice)
-constexpr int kPFloats = kPRows * kTile;
+// Y (stage 1 -> stage 2) is PRIVATE to a warp: the warp that transforms the frame pairs (wg, kGroupWarps + wg) in stage 1
+// also runs all 13 slots of those two pairs in stage 2 (lane = 2 slot + q, 26 lanes), so the hand-over is a __syncwarp,
+// not a barrier over the group.  Per warp: [n1][Re: 13 slots x 2 pairs | Im: 13 x 2] float2, rows of 53 (odd: the 16 n1
+// lanes of a stage-1 store hit 16 different 8-byte banks; stage 2 reads 26 consecutive float2).  Im of slot 0 is zero.
+constexpr int kYLanes = 2 * fft::kNumSlots;                    // 26 (slot, q) combinations = lanes of stage 2
+constexpr int kYN1 = 2 * kYLanes + 1;                          // 53 float2 per n1 row
+constexpr int kYWarpFloat2 = 16 * kYN1;                        // 848 float2 = 6,784 B per warp
+constexpr int kYFloat2 = kGroupWarps * kYWarpFloat2;
+// P (stage 2 -> mel), per group: [pair][kPPair] float2 with the power of (slot, FFT16 output position i) at 13 i + slot
+constexpr int kPRows = fft::kNumSlots * 16;                    // 208 (201 distinct bins; slot 0 holds seven of its bins twice)
+constexpr int kPPair = kPRows + (kPairs == 16 ? 1 : 2);        // 209 (= 1 mod 16) / 210 (8 pairs: 4 x 210 = 8 mod 16)
+constexpr int kPFloats = 2 * kPairs * kPPair;
 
 constexpr int kSmemRaw = kRawFloats * 4;        // 22,400
-constexpr int kSmemY = kYFloat2 * 8;            // 53,376
-constexpr int kSmemP = kPFloats * 4;            // 26,624
+constexpr int kSmemY = kYFloat2 * 8;
+constexpr int kSmemP = kPFloats * 4;
 constexpr int kSmemGroup = kSmemRaw + kSmemY + kSmemP;
 constexpr int kSmemMisc = 512;
 constexpr int kSmemBytes = kGroups * kSmemGroup + kSmemMisc;
@@ -96,9 +99,14 @@ constexpr int kMaxFiltersPerWarp = 16;          // 8 warps x 16 >= 128 mels
 constexpr int kMaxGroupBins = 16;               // bins between two adjacent filter centres
 constexpr int kTmemColsPerTile = kMaxFiltersPerWarp;                          // 16 (lane = frame)
 constexpr int kTmemColsPerWarp = kMaxTilesPerGroup * kTmemColsPerTile;        // 128; 4 warps per lane quarter = 512 columns
-constexpr int kS2Warps = (fft::kNumSlots + 1) / 2;                            // 7 warps of a group run stage 2 (two slots each)
 static_assert(4 * kTmemColsPerWarp <= 512, "the retained mel power must fit the 512 TMEM columns");
 static_assert(kVCluster <= 32, "max reduction over the cluster uses one warp");
+
+// float2 index, inside a pair's row of P, of FFT bin k (stage 2 stores position i of slot s at 13 i + s)
+__host__ __device__ __forceinline__ int p_index_of_bin(int k) {
+    const int row = fft::row_of_bin(k);        // 16 slot + position
+    return 13 * (row & 15) + (row >> 4);
+}
 
 // Everything the kernel reads with warp-uniform indices, passed by value (constant bank).
 //
@@ -137,7 +145,7 @@ inline int build_tables(const MelSparse& sp, int n_mels, Tables* t, int* variant
     mp.n_mels = (int16_t)n_mels;
     for (int k = 0; k < kNFreq; ++k) {
         mp.w2[k] = make_float2(sp.w_lo[k], sp.w_hi[k]);
-        mp.prow[k] = (int16_t)fft::row_of_bin(k);
+        mp.prow[k] = (int16_t)p_index_of_bin(k);
     }
     // first bin of every group: gstart[v] = first k with lo[k] >= v - 1   (v = lo + 1 in 0..n_mels)
     int gstart[kMaxMels + 2];
@@ -420,35 +428,40 @@ __device__ __forceinline__ void stage1(const float* raw, float2* Y, const float 
     fft::rfft25<V2>(y, out);
 #endif
     before_store();
-    float2* yo = Y + n1 * kYN1 + (8 * sub + wg);
-    yo[0] = out[0].v;
+    float2* yo = Y + n1 * kYN1 + sub;             // (Y = this warp's private buffer; q = sub)
+    yo[0] = out[0].v;                             // slot 0: Re only
 #pragma unroll
-    for (int c = 1; c < 25; ++c) yo[(c + 1) * kPairs] = out[c].v;     // slot s >= 1: Re at component 2 s, Im at 2 s + 1
+    for (int sl = 1; sl < fft::kNumSlots; ++sl) {
+        yo[2 * sl] = out[2 * sl - 1].v;           // Re of slot sl
+        yo[kYLanes + 2 * sl] = out[2 * sl].v;     // Im
+    }
 }
 
 // ---- stage 2 ----------------------------------------------------------------------------------
-// half warp = one k2 slot (lane-varying: only two base addresses depend on it), lane & 15 = frame pair.
-// The power of FFT16 output position i goes to row 16 slot + i of P (fft::row_of_bin inverts that for the mel stage).
-// `loaded()` runs once Y has been read, `before_store()` just before P is written.
-template <class Loaded, class BeforeStore>
-__device__ __forceinline__ void stage2(const float2* Y, float* P, int slot, int pair, Loaded loaded, BeforeStore before_store) {
-    const float2* yl = Y + 2 * slot * kPairs + pair;
+// lane = 2 slot + q (26 of 32 lanes; the last six repeat lane 25): the 16-point complex DFT over n1 of slot `slot` for
+// the warp's own frame pair q, then |X|^2.  The slot only selects base addresses, so it varies inside the warp for free.
+// The power of FFT16 output position i goes to float2 13 i + slot of the pair's row of P (p_index_of_bin inverts that
+// for the mel stage).  `before_store()` runs just before P is written.
+template <class BeforeStore>
+__device__ __forceinline__ void stage2(const float2* Y, float* P, int wg, int lane, BeforeStore before_store) {
+    const int sl = min(lane, kYLanes - 1);
+    const int slot = sl >> 1, q = sl & 1;
+    const float2* yl = Y + sl;
     V2 xr[16], xi[16];
 #pragma unroll
     for (int n1 = 0; n1 < 16; ++n1) {
         xr[n1].v = yl[n1 * kYN1];
-        xi[n1].v = yl[n1 * kYN1 + kPairs];       // slot 0 (k2 = 0, purely real Y): the zero component
+        xi[n1].v = yl[n1 * kYN1 + kYLanes];      // slot 0 (k2 = 0, purely real Y): zeros, written once
     }
-    loaded();
 #ifndef WLM_KO_S2FFT
     fft::cfft16<V2>(xr, xi);
 #endif
     before_store();
-    float2* pl = reinterpret_cast<float2*>(P + slot * 16 * kTile) + pair;
+    float2* pl = reinterpret_cast<float2*>(P) + (wg + kGroupWarps * q) * kPPair + slot;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
         const V2 pw = vfma(xr[i], xr[i], vmul(xi[i], xi[i]));
-        pl[i * kPairs] = pw.v;
+        pl[13 * i] = pw.v;
     }
 }
 
@@ -461,7 +474,7 @@ __device__ __forceinline__ void stage2(const float2* Y, float* P, int slot, int 
 #define WLM_MEL_TERM(i)                                                            \
     case (i) + 1: {                                                                \
         const float2 w = ww[i];                                                    \
-        const float pv = pl[pr[i] * kTile];                                        \
+        const float pv = pl[2 * pr[i]];                                            \
         A = fmaf(pv, w.y, A);                                                      \
         Bq = fmaf(pv, w.x, Bq);                                                    \
     }
@@ -469,7 +482,7 @@ __device__ __forceinline__ void stage2(const float2* Y, float* P, int slot, int 
 // table-driven variant (any bank that fits the sparse form)
 __device__ __forceinline__ float mel_stage(const KernelTables& kt, const float* P, int wg, int lane, uint32_t tcol) {
     const int nf = kt.nf[wg];
-    const float* pl = P + lane;
+    const float* pl = P + (lane >> 1) * (2 * kPPair) + (lane & 1);      // this frame's row of P
     float out[kMaxFiltersPerWarp];
 #pragma unroll
     for (int q = 0; q < kMaxFiltersPerWarp; ++q) out[q] = 0.f;
@@ -520,7 +533,7 @@ template <int NMELS, int W>
 __device__ __forceinline__ float mel_fixed_warp(const KernelTables& kt, const float* P, int lane, uint32_t tcol) {
     using S = MelFixed<NMELS>;
     constexpr int nf = S::nf(W), m0 = S::m0(W);
-    const float* pl = P + lane;
+    const float* pl = P + (lane >> 1) * (2 * kPPair) + (lane & 1);      // this frame's row of P
     float out[kMaxFiltersPerWarp];
 #pragma unroll
     for (int q = 0; q < kMaxFiltersPerWarp; ++q) out[q] = 0.f;
@@ -529,7 +542,7 @@ __device__ __forceinline__ float mel_fixed_warp(const KernelTables& kt, const fl
 #pragma unroll
         for (int k = S::gstart(m0 + g); k < S::gstart(m0 + g + 1); ++k) {
             const float2 w = kt.w2[k];
-            const float pv = pl[fft::row_of_bin(k) * kTile];
+            const float pv = pl[2 * p_index_of_bin(k)];
             if (g < nf) out[g] = fmaf(pv, w.y, out[g]);            // rising side of m0+g
             if (g > 0) out[g - 1] = fmaf(pv, w.x, out[g - 1]);     // falling side of m0+g-1
         }
@@ -596,16 +609,14 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
 
     unsigned char* gbase = smem + grp * kSmemGroup;
     float* raw = reinterpret_cast<float*>(gbase);
-    float2* Y = reinterpret_cast<float2*>(gbase + kSmemRaw);
+    float2* Y = reinterpret_cast<float2*>(gbase + kSmemRaw) + wg * kYWarpFloat2;      // this WARP's stage-1 output
     float* P = reinterpret_cast<float*>(gbase + kSmemRaw + kSmemY);
     unsigned char* misc = smem + kGroups * kSmemGroup;
     // mbarriers (8 B each), one set per group.  No CTA- or group-wide barrier separates the stages of a
     // tile: every hand-over between warps is one of these, so warps drift apart.
     unsigned char* gm = misc + grp * 64;
     const uint32_t bar_raw = smem_u32(gm);           // TMA landed the half-tile's PCM              (tx, 1 arrival)
-    const uint32_t bar_yfull = smem_u32(gm + 8);     // all 8 warps stored stage-1 output           (8)
-    const uint32_t bar_yfree = smem_u32(gm + 16);    // all 7 stage-2 warps have read Y             (7)
-    const uint32_t bar_pfull = smem_u32(gm + 24);    // all 7 stage-2 warps stored the power        (7)
+    const uint32_t bar_pfull = smem_u32(gm + 24);    // all warps of the group stored the power of the half-tile
     const uint32_t bar_pfree = smem_u32(gm + 32);    // all 8 warps finished the mel stage          (8)
     uint32_t* raw_readers = reinterpret_cast<uint32_t*>(gm + 40);     // warps done with the raw buffer
     // clip-end max exchange (all indexed by clip parity): every virtual CTA of the cluster delivers its max into
@@ -626,9 +637,7 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
         for (int g = 0; g < kGroups; ++g) {
             const uint32_t b = smem_u32(misc + g * 64);
             mbar_init(b, 1);
-            mbar_init(b + 8, kGroupWarps);
-            mbar_init(b + 16, kS2Warps);
-            mbar_init(b + 24, kS2Warps);
+            mbar_init(b + 24, kGroupWarps);
             mbar_init(b + 32, kGroupWarps);
             *reinterpret_cast<uint32_t*>(misc + g * 64 + 40) = 0;
         }
@@ -642,8 +651,9 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
     cluster.sync();     // (also a CTA barrier) every peer's mbarriers exist before anyone can arrive on them remotely
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
-    // the zero component of Y (imaginary part of slot 0): written once, ordered before the first stage 2 by bar_yfull
-    Y[((tid & (kGroupThreads - 1)) >> 4) * kYN1 + kPairs + (tid & 15)] = make_float2(0.f, 0.f);
+    // the imaginary part of slot 0 in the warp's Y: zeros, written once (stage 1 never stores there)
+    Y[(lane >> 1) * kYN1 + kYLanes + (lane & 1)] = make_float2(0.f, 0.f);
+    __syncwarp();
     // this warp's TMEM window: lane quarter (warp & 3), 128 columns at (warp >> 2) * 128
     const uint32_t twin = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) +
                           static_cast<uint32_t>((warp >> 2) * kTmemColsPerWarp);
@@ -653,8 +663,6 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
     float wv[25];
 #pragma unroll
     for (int t = 0; t < 25; ++t) wv[t] = win_lane[n1 * 25 + t];
-    // stage 2: slot of this half warp (warp 6's upper half repeats slot 12: same loads, same stores)
-    const int slot = min(2 * wg + (lane >> 4), fft::kNumSlots - 1);
 
     // The group's work is a stream of steps, one per half-tile it owns (a clip in which it owns no active
     // half-tile still contributes one empty step so that it takes part in that clip's cluster barrier).
@@ -731,17 +739,13 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
                                issue_next_tile(cb, cc, cn_my, cj);
                            }
                        }
-                       // stage 2 of the previous half-tile must have read Y (long done: waiting here, before the
-                       // FFT, lets the stores below interleave with its tail)
                        WLM_TR(tnum, 2);
-                       if (tnum > 0) mbar_wait(bar_yfree, (tnum - 1) & 1);
                        WLM_TR(tnum, 3);
                    },
                    [&]() {
                        WLM_TR(tnum, 4);
                    });
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_yfull);
+            __syncwarp();      // Y is private to the warp: this is the whole stage 1 -> stage 2 hand-over
             WLM_TR(tnum, 5);
         }
         // ---- F: output of the clip that ended one step ago, ONE retained half-tile per step ----------------------
@@ -863,21 +867,15 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
             pend_b = pb;
             pend_n_my = pn_my;
         }
-        // ---- C: stage 2 ----------------------------------------------------------------------------------
-        if (do_tile && wg < kS2Warps) {
+        // ---- C: stage 2 (every warp, on its own two frame pairs) ------------------------------------------
+        if (do_tile) {
             WLM_TR(tnum, 6);
-            mbar_wait(bar_yfull, tnum & 1);
             WLM_TR(tnum, 7);
-            stage2(Y, P, slot, lane & 15,
-                   [&]() {
-                       __syncwarp();
-                       if (lane == 0) mbar_arrive(bar_yfree);   // phase tnum
-                       // the mel stage of the previous half-tile must have read P (all 8 warps)
-                       if (tnum > 0) mbar_wait(bar_pfree, (tnum - 1) & 1);
-                       WLM_TR(tnum, 8);
-                   },
-                   [&]() {
-                   });
+            stage2(Y, P, wg, lane, [&]() {
+                WLM_TR(tnum, 8);
+                // the mel stage of the previous half-tile must have read P (all warps of the group)
+                if (tnum > 0) mbar_wait(bar_pfree, (tnum - 1) & 1);
+            });
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_pfull);   // phase tnum
             WLM_TR(tnum, 9);
