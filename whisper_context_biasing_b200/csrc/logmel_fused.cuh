@@ -7,21 +7,20 @@
 //   TMA (cp.async.bulk, mbarrier)  raw PCM  ->  shared memory, two sub-regions 16 banks apart
 //   stage 1  per warp: 4 frames x 16 sub-transforms; lane = (n1, sub-region); 25-point real DFT of
 //            the Hann-windowed samples n = (25 n1 + 16 n2) mod 400, packed f32x2 over two frames
-//   stage 2  per HALF warp: one k2 slot for 16 frame pairs; 16-point complex DFT over n1, |X|^2
+//   stage 2  the SAME warp, on its own two frame pairs: lane = (k2 slot, pair), 26 lanes; 16-point
+//            complex DFT over n1, |X|^2.  The hand-over is a __syncwarp (Y is private to the warp).
 //   mel      per warp: a run of <= 16 filters, lane = frame; sparse gather; mel POWER retained in
 //            TENSOR MEMORY (tcgen05.st), running max in registers
 //
 // with the prime-factor index maps of fft_pfa.cuh (no twiddles between the stages).  The FFT
 // arithmetic is FADD2 / FMUL2 / FFMA2 on (frame a, frame b) pairs with immediate constants.
-// The two groups share nothing but the cluster barrier: they are started out of phase, so the
-// shared-memory-bound passes of one group (loads / stores around each FFT) run under the FMA-bound
-// passes of the other -- one group alone serialises them (measured: LDS.64 costs two shared-memory
-// cycles per SM, FADD2 two FMA-pipe cycles per scheduler; tools/ubench_issue.cu).
-// When the clip is done the 12 virtual CTAs exchange their maxima through distributed shared memory
-// (one cluster barrier), and a single pass reads the retained mel power back (tcgen05.ld) and writes
+// The two groups share nothing but the clip-end exchange.  When the clip is done the 12 virtual
+// CTAs deliver their maxima to each other through distributed shared memory (st.async completing
+// bytes on the receiver's mbarrier: nobody waits), and the retained mel power is read back
+// (tcgen05.ld) one half-tile per step of the NEXT clip and written as
 // (max(log10(max(p,1e-10)), gmax - 8) + 4) / 4 -- the features touch HBM exactly once.
 //
-// Shared memory (bytes):  raw 2 x 22,400 | Y 2 x 53,376 | P 2 x 26,624 | mbarriers + scratch 512
+// Shared memory (bytes):  raw 2 x 22,400 | Y 2 x 54,272 | P 2 x 26,752 | mbarriers + scratch 1024
 #pragma once
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
@@ -60,10 +59,10 @@ constexpr int kGroupWarps = 8;
 constexpr int kGroupThreads = kGroupWarps * 32;
 constexpr int kWarps = kGroups * kGroupWarps;
 constexpr int kThreads = kWarps * 32;
-constexpr int kTile = 32;                 // frames per half-tile (the unit of work of one group)
+constexpr int kTile = 4 * kGroupWarps;    // frames per half-tile (the unit of work of one group): 2 pairs per warp
 constexpr int kPairs = kTile / 2;         // 16 frame pairs
 constexpr int kTilesPerClip = (kNFrames + kTile - 1) / kTile;  // 94
-constexpr int kSubFrames = 16;                                 // frames per raw sub-region
+constexpr int kSubFrames = kTile / 2;                          // frames per raw sub-region
 constexpr int kSubLen = (kSubFrames - 1) * kHop + kNfft;       // 2800 samples (= 16 mod 32: sub-regions 16 banks apart)
 constexpr int kSubStep = kSubFrames * kHop;                    // 2560: sub-region 1 starts 16 frames later
 constexpr int kRawFloats = 2 * kSubLen;                        // 5600 per group
@@ -88,7 +87,7 @@ constexpr int kSmemRaw = kRawFloats * 4;        // 22,400
 constexpr int kSmemY = kYFloat2 * 8;
 constexpr int kSmemP = kPFloats * 4;
 constexpr int kSmemGroup = kSmemRaw + kSmemY + kSmemP;
-constexpr int kSmemMisc = 512;
+constexpr int kSmemMisc = 1024;
 constexpr int kSmemBytes = kGroups * kSmemGroup + kSmemMisc;
 static_assert(kSmemRaw % 128 == 0 && kSmemY % 128 == 0 && kSmemP % 128 == 0, "buffers stay 128-byte aligned");
 
@@ -605,7 +604,7 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler
-    const int grp = warp >> 3, wg = warp & 7;                 // warp group and warp inside the group
+    const int grp = warp / kGroupWarps, wg = warp % kGroupWarps;   // warp group and warp inside the group
 
     unsigned char* gbase = smem + grp * kSmemGroup;
     float* raw = reinterpret_cast<float*>(gbase);
@@ -621,11 +620,11 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
     uint32_t* raw_readers = reinterpret_cast<uint32_t*>(gm + 40);     // warps done with the raw buffer
     // clip-end max exchange (all indexed by clip parity): every virtual CTA of the cluster delivers its max into
     // clip_max of EVERY CTA (distributed shared memory, st.async) which completes bytes on that CTA's bar_max
-    const uint32_t bar_max = smem_u32(misc + 128);                    // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 144);    // TMEM base address
-    uint32_t* grp_cnt = reinterpret_cast<uint32_t*>(misc + 160);      // [2][2] warps of the group that have contributed
-    int* grp_max = reinterpret_cast<int*>(misc + 176);                // [2][2] running max of the group (float bits, >= 0)
-    float* clip_max = reinterpret_cast<float*>(misc + 192);           // [2][12] written by the peers
+    const uint32_t bar_max = smem_u32(misc + 256);                    // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 272);    // TMEM base address
+    uint32_t* grp_cnt = reinterpret_cast<uint32_t*>(misc + 288);      // [2][kGroups] warps of the group that have contributed
+    int* grp_max = reinterpret_cast<int*>(misc + 320);                // [2][kGroups] running max of the group (float bits, >= 0)
+    float* clip_max = reinterpret_cast<float*>(misc + 352);           // [2][kVCluster] written by the peers
 
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = static_cast<int>(cluster.block_rank());
@@ -643,7 +642,7 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
         }
         mbar_init(bar_max, 1);          // one arrival (this CTA's group 0, with the byte count) + 12 x 4 bytes from the peers
         mbar_init(bar_max + 8, 1);
-        for (int i = 0; i < 4; ++i) { grp_cnt[i] = 0; grp_max[i] = 0; }
+        for (int i = 0; i < 2 * kGroups; ++i) { grp_cnt[i] = 0; grp_max[i] = 0; }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) tmem_alloc_512(smem_u32(tmem_slot));
@@ -784,8 +783,7 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
                 WLM_TRC(fin_seq, 2);
                 float pmax = lane < kVCluster ? clip_max[fpar * kVCluster + lane] : 0.f;
 #pragma unroll
-                for (int o = 8; o > 0; o >>= 1) pmax = fmaxf(pmax, __shfl_xor_sync(0xffffffffu, pmax, o));
-                pmax = __shfl_sync(0xffffffffu, pmax, 0);
+                for (int o = 16; o > 0; o >>= 1) pmax = fmaxf(pmax, __shfl_xor_sync(0xffffffffu, pmax, o));
                 ++fin_seq;
                 have_max = true;
                 const float gmax = log10_floor(pmax);                 // TF-FE:157
