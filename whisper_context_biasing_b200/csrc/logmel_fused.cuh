@@ -576,17 +576,20 @@ __device__ __forceinline__ float log10_floor(float p) {
 // Debug timeline (-DWLM_TRACE): CTA 0 stamps clock64() at the phase boundaries of its first 48 half-tiles per warp;
 // wlm_debug_trace() copies the buffer out.  [warp][tile ordinal][event]
 #ifdef WLM_TRACE
+#ifndef WLM_TRACE_CTA
+#define WLM_TRACE_CTA 0
+#endif
 constexpr int kTraceTiles = 48, kTraceEvents = 12;
 __device__ unsigned long long g_trace[kWarps * kTraceTiles * kTraceEvents];
 #define WLM_TR(tn, e)                                                                              \
     do {                                                                                           \
-        if (blockIdx.x == 0 && (tn) < kTraceTiles && lane == 0)                                    \
+        if (blockIdx.x == WLM_TRACE_CTA && (tn) < kTraceTiles && lane == 0)                                    \
             g_trace[(warp * kTraceTiles + (tn)) * kTraceEvents + (e)] = clock64();                 \
     } while (0)
 __device__ unsigned long long g_trace_clip[kWarps * 8 * 4];      // [warp][clip seq][D, wait begin, wait end, -]
 #define WLM_TRC(seq, e)                                                                            \
     do {                                                                                           \
-        if (blockIdx.x == 0 && (seq) < 8 && lane == 0) g_trace_clip[(warp * 8 + (seq)) * 4 + (e)] = clock64(); \
+        if (blockIdx.x == WLM_TRACE_CTA && (seq) < 8 && lane == 0) g_trace_clip[(warp * 8 + (seq)) * 4 + (e)] = clock64(); \
     } while (0)
 #else
 #define WLM_TR(tn, e)
