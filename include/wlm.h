@@ -119,6 +119,10 @@ size_t wlm_workspace_bytes(const wlm_plan* plan, int B);
  *   offsets_dev   NULL  -> clip b starts at element b*row_stride (dense [B,row_stride] layout;
  *                          row_stride must be a multiple of 4 elements);
  *                 else  -> device int64[B], clip b starts at element offsets_dev[b] (ragged).
+ *                          Every start must be 16-byte aligned (a multiple of 4 float32 / 8 int16
+ *                          elements), and the buffer must be readable up to the next 16-byte
+ *                          boundary after the last sample of every clip: the bulk copies move whole
+ *                          16-byte units (what lies between lengths[b] and that boundary is ignored).
  *   lengths_dev   NULL  -> every clip has min(row_stride, 480000) valid samples (dense only);
  *                 else  -> device int32[B], valid samples of clip b (any value >= 0; values
  *                          above 480000 are truncated, the rest is right-padded with zeros,

@@ -1,5 +1,9 @@
+"""Launch time against batch size: marginal time per round of 22 clips (one per co-resident cluster) and the fixed cost per
+launch (prologue, first TMA, read-back of the last clip).  B = 22 / 44 keep the PCM inside the 126 MB L2: same round time as
+the HBM-resident sizes, i.e. the kernel does not wait for HBM.
+    python tools/round_time.py"""
 import sys, os, torch
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from whisper_context_biasing_b200 import B200WhisperFeatureExtractor
 fe = B200WhisperFeatureExtractor(feature_size=80)
 g = torch.Generator(device="cuda").manual_seed(0)
