@@ -614,8 +614,8 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
     float2* Y = reinterpret_cast<float2*>(gbase + kSmemRaw) + wg * kYWarpFloat2;      // this WARP's stage-1 output
     float* P = reinterpret_cast<float*>(gbase + kSmemRaw + kSmemY);
     unsigned char* misc = smem + kGroups * kSmemGroup;
-    // mbarriers (8 B each), one set per group.  No CTA- or group-wide barrier separates the stages of a
-    // tile: every hand-over between warps is one of these, so warps drift apart.
+    // mbarriers (8 B each), one set per group.  Inside a warp stage 1 hands over to stage 2 through the warp's own Y
+    // (__syncwarp); between warps there are only these: the shared raw buffer and the shared P buffer of the group.
     unsigned char* gm = misc + grp * 64;
     const uint32_t bar_raw = smem_u32(gm);           // TMA landed the half-tile's PCM              (tx, 1 arrival)
     const uint32_t bar_pfull = smem_u32(gm + 24);    // all warps of the group stored the power of the half-tile
@@ -667,13 +667,13 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
     for (int t = 0; t < 25; ++t) wv[t] = win_lane[n1 * 25 + t];
 
     // The group's work is a stream of steps, one per half-tile it owns (a clip in which it owns no active
-    // half-tile still contributes one empty step so that it takes part in that clip's cluster barrier).
+    // half-tile still contributes one empty step so that it takes part in that clip's max exchange).
     // Program order of every warp in step i (half-tile t_i):
-    //   A  stage 1 of t_i            wait raw | load | last warp re-arms TMA | FFT | wait Y free | store | arrive Y full
+    //   A  stage 1 of t_i            wait raw | load | last warp re-arms TMA | FFT | store (warp-private Y) | __syncwarp
     //   F  output pass of the clip that ended one step ago   (wait for the 12 maxima, TMEM read-back, stores)
     //   B  mel stage of t_{i-1}      wait P full | ... | arrive P free
     //   D  if t_{i-1} ended a clip:  warp max -> group max (atomic); the last warp delivers it to all 6 CTAs
-    //   C  stage 2 of t_i (7 warps)  wait Y full | load | arrive Y free | FFT | wait P free | store | arrive P full
+    //   C  stage 2 of t_i            load own Y | FFT | wait P free | store | arrive P full
     // `c*` = the step whose half-tile is in stage 1 / stage 2, `p*` = the previous step (mel stage).
     auto my_tiles = [&](int n_act) { return n_act > vrank ? (n_act - vrank + kVCluster - 1) / kVCluster : 0; };
     int cb = cluster_id, cj = 0, cn_my = 0;          // clip, step inside the clip, half-tiles of mine in the clip
