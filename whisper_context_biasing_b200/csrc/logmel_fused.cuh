@@ -479,7 +479,8 @@ __device__ __forceinline__ void stage2(const float2* Y, float* P, int wg, int la
     }
 
 // table-driven variant (any bank that fits the sparse form)
-__device__ __forceinline__ float mel_stage(const KernelTables& kt, const float* P, int wg, int lane, uint32_t tcol) {
+template <class Sink>
+__device__ __forceinline__ float mel_stage(const KernelTables& kt, const float* P, int wg, int lane, Sink sink) {
     const int nf = kt.nf[wg];
     const float* pl = P + (lane >> 1) * (2 * kPPair) + (lane & 1);      // this frame's row of P
     float out[kMaxFiltersPerWarp];
@@ -504,7 +505,7 @@ __device__ __forceinline__ float mel_stage(const KernelTables& kt, const float* 
             if (g > 0) out[g - 1] += Bq;                     // falling side of filter m0+g-1
         }
     }
-    tmem_st_x16(tcol, out);
+    sink(out);          // the 16 mel powers of this lane's frame: tensor memory (cluster kernel) or HBM (flat kernel)
     float mx = 0.f;
 #pragma unroll
     for (int q = 0; q < kMaxFiltersPerWarp; ++q)
@@ -528,8 +529,8 @@ template <> struct MelFixed<128> {
     static __device__ __forceinline__ constexpr int nf(int w) { return kMelNf_128[w]; }
 };
 
-template <int NMELS, int W>
-__device__ __forceinline__ float mel_fixed_warp(const KernelTables& kt, const float* P, int lane, uint32_t tcol) {
+template <int NMELS, int W, class Sink>
+__device__ __forceinline__ float mel_fixed_warp(const KernelTables& kt, const float* P, int lane, Sink sink) {
     using S = MelFixed<NMELS>;
     constexpr int nf = S::nf(W), m0 = S::m0(W);
     const float* pl = P + (lane >> 1) * (2 * kPPair) + (lane & 1);      // this frame's row of P
@@ -546,24 +547,24 @@ __device__ __forceinline__ float mel_fixed_warp(const KernelTables& kt, const fl
             if (g > 0) out[g - 1] = fmaf(pv, w.x, out[g - 1]);     // falling side of m0+g-1
         }
     }
-    tmem_st_x16(tcol, out);
+    sink(out);          // the 16 mel powers of this lane's frame: tensor memory (cluster kernel) or HBM (flat kernel)
     float mx = 0.f;
 #pragma unroll
     for (int q = 0; q < nf; ++q) mx = fmaxf(mx, out[q]);
     return mx;
 }
 
-template <int NMELS>
-__device__ __forceinline__ float mel_fixed(const KernelTables& kt, const float* P, int wg, int lane, uint32_t tcol) {
+template <int NMELS, class Sink>
+__device__ __forceinline__ float mel_fixed(const KernelTables& kt, const float* P, int wg, int lane, Sink sink) {
     switch (wg) {
-        case 0: return mel_fixed_warp<NMELS, 0>(kt, P, lane, tcol);
-        case 1: return mel_fixed_warp<NMELS, 1>(kt, P, lane, tcol);
-        case 2: return mel_fixed_warp<NMELS, 2>(kt, P, lane, tcol);
-        case 3: return mel_fixed_warp<NMELS, 3>(kt, P, lane, tcol);
-        case 4: return mel_fixed_warp<NMELS, 4>(kt, P, lane, tcol);
-        case 5: return mel_fixed_warp<NMELS, 5>(kt, P, lane, tcol);
-        case 6: return mel_fixed_warp<NMELS, 6>(kt, P, lane, tcol);
-        default: return mel_fixed_warp<NMELS, 7>(kt, P, lane, tcol);
+        case 0: return mel_fixed_warp<NMELS, 0>(kt, P, lane, sink);
+        case 1: return mel_fixed_warp<NMELS, 1>(kt, P, lane, sink);
+        case 2: return mel_fixed_warp<NMELS, 2>(kt, P, lane, sink);
+        case 3: return mel_fixed_warp<NMELS, 3>(kt, P, lane, sink);
+        case 4: return mel_fixed_warp<NMELS, 4>(kt, P, lane, sink);
+        case 5: return mel_fixed_warp<NMELS, 5>(kt, P, lane, sink);
+        case 6: return mel_fixed_warp<NMELS, 6>(kt, P, lane, sink);
+        default: return mel_fixed_warp<NMELS, 7>(kt, P, lane, sink);
     }
 }
 
@@ -600,11 +601,19 @@ __device__ unsigned long long g_trace_clip[kWarps * 8 * 4];      // [warp][clip 
 // The kernel: persistent clusters of 6 CTAs x 2 warp groups, one clip per cluster at a time.
 // ================================================================================================
 // NMELS = 80 / 128: unrolled mel stage for the Whisper banks; NMELS = 0: table-driven mel stage.
-template <int NMELS>
+//
+// FLAT = true is the same pipeline for the SMs that 6-CTA clusters cannot cover (clusters do not span GPCs: 22 of them fit,
+// 16 SMs stay idle; tools/ubench_corun.cu shows that a second kernel runs there undisturbed).  One CTA per clip, no cluster
+// and no tensor memory: the mel stage writes (log10 + 4) / 4 straight to HBM, and when the clip is done the CTA's 16 warps
+// meet once, take the clip's max and re-read the clip's 0.96 MB from L2 to apply the max - 8 clamp.
+template <int NMELS, bool FLAT>
 __global__ void __launch_bounds__(kThreads, 1)
 logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt, const float* __restrict__ win_lane) {
     namespace cg = cooperative_groups;
+    constexpr int kVC = FLAT ? kGroups : kVCluster;      // virtual CTAs (warp groups) that share a clip
     extern __shared__ __align__(128) unsigned char smem[];
+    // this CTA is resident: once all of them are, the flat kernel (a programmatic dependent launch) may take the free SMs
+    if constexpr (!FLAT) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler
     const int grp = warp / kGroupWarps, wg = warp % kGroupWarps;   // warp group and warp inside the group
@@ -630,10 +639,13 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
     float* clip_max = reinterpret_cast<float*>(misc + 352);           // [2][kVCluster] written by the peers
 
     cg::cluster_group cluster = cg::this_cluster();
-    const int rank = static_cast<int>(cluster.block_rank());
+    const int rank = FLAT ? 0 : static_cast<int>(cluster.block_rank());
     const int vrank = rank * kGroups + grp;          // virtual CTA inside the clip
-    const int cluster_id = blockIdx.x / kCluster;
-    const int n_clusters = gridDim.x / kCluster;
+    const int cluster_id = FLAT ? static_cast<int>(blockIdx.x) : static_cast<int>(blockIdx.x) / kCluster;
+    const int n_clusters = FLAT ? static_cast<int>(gridDim.x) : static_cast<int>(gridDim.x) / kCluster;
+    // flat kernel: clip-end meeting of the CTA's 16 warps and the clip's max (ring of three: see D)
+    const uint32_t bar_clip = smem_u32(misc + 640);
+    int* flat_max = reinterpret_cast<int*>(misc + 656);
 
     if (tid == 0) {
         for (int g = 0; g < kGroups; ++g) {
@@ -646,13 +658,20 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
         mbar_init(bar_max, 1);          // one arrival (this CTA's group 0, with the byte count) + 12 x 4 bytes from the peers
         mbar_init(bar_max + 8, 1);
         for (int i = 0; i < 2 * kGroups; ++i) { grp_cnt[i] = 0; grp_max[i] = 0; }
+        mbar_init(bar_clip, kWarps);
+        flat_max[0] = flat_max[1] = flat_max[2] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) tmem_alloc_512(smem_u32(tmem_slot));
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    cluster.sync();     // (also a CTA barrier) every peer's mbarriers exist before anyone can arrive on them remotely
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_base = *tmem_slot;
+    uint32_t tmem_base = 0;
+    if constexpr (FLAT) {
+        __syncthreads();
+    } else {
+        if (warp == 0) tmem_alloc_512(smem_u32(tmem_slot));
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        cluster.sync();     // (also a CTA barrier) every peer's mbarriers exist before anyone can arrive on them remotely
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        tmem_base = *tmem_slot;
+    }
     // the imaginary part of slot 0 in the warp's Y: zeros, written once (stage 1 never stores there)
     Y[(lane >> 1) * kYN1 + kYLanes + (lane & 1)] = make_float2(0.f, 0.f);
     __syncwarp();
@@ -675,8 +694,8 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
     //   D  if t_{i-1} ended a clip:  warp max -> group max (atomic); the last warp delivers it to all 6 CTAs
     //   C  stage 2 of t_i            load own Y | FFT | wait P free | store | arrive P full
     // `c*` = the step whose half-tile is in stage 1 / stage 2, `p*` = the previous step (mel stage).
-    auto my_tiles = [&](int n_act) { return n_act > vrank ? (n_act - vrank + kVCluster - 1) / kVCluster : 0; };
-    int cb = cluster_id, cj = 0, cn_my = 0;          // clip, step inside the clip, half-tiles of mine in the clip
+    auto my_tiles = [&](int n_act) { return n_act > vrank ? (n_act - vrank + kVC - 1) / kVC : 0; };
+    int cb = a.clip_first + cluster_id, cj = 0, cn_my = 0;          // clip, step inside the clip, half-tiles of mine in the clip
     bool cvalid = cb < a.B;
     ClipCtx cc;
     cc.b = cb; cc.len = 0; cc.n_act = 0; cc.base = 0;
@@ -685,12 +704,13 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
         cn_my = my_tiles(cc.n_act);
     }
     bool pvalid = false, phas = false, plast = false;
-    int pb = 0, pj = 0, ptile = 0, pn_my = 0;
+    int pb = 0, pj = 0, ptile = 0, pn_my = 0, pn_act = 0;
+    int clip_seq = 0;                        // (flat kernel) clips this warp has finished
     // TMA target after (clip cb0, step j0): the next half-tile of the same clip, else the first half-tile of
     // the next clip in which this group owns one.  Executed by ONE lane (the last warp to finish reading raw).
     auto issue_next_tile = [&](int cb0, const ClipCtx& c0, int n_my0, int j0) {
         if (j0 + 1 < n_my0) {
-            tile_issue_tma(a, c0, vrank + (j0 + 1) * kVCluster, raw, bar_raw);
+            tile_issue_tma(a, c0, vrank + (j0 + 1) * kVC, raw, bar_raw);
             return;
         }
         for (int nb = cb0 + n_clusters; nb < a.B; nb += n_clusters) {
@@ -721,7 +741,7 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
 
     while (cvalid || pvalid || pend) {
         const bool do_tile = cvalid && cj < cn_my;
-        const int ctile = vrank + cj * kVCluster;
+        const int ctile = vrank + cj * kVC;
         // ---- A: stage 1 ----------------------------------------------------------------------------
         if (do_tile) {
             WLM_TR(tnum, 0);
@@ -759,7 +779,7 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
             float r[16];
             tmem_wait_st();
             tmem_ld_x16(twin + j * kTmemColsPerTile, r);
-            const int f0 = (vrank + j * kVCluster) * kTile;
+            const int f0 = (vrank + j * kVC) * kTile;
             float* of = a.out + (static_cast<int64_t>(pend_b) * a.n_mels + kt.m0[wg]) * kNFrames + lane + f0;
             const bool va = f0 + lane < kNFrames;
             // rows in blocks of four: straight-line code inside a block, so four MUFU.LG2 chains overlap
@@ -778,7 +798,7 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
                 }
             }
         };
-        if (pend) {
+        if (!FLAT && pend) {
             if (!have_max) {    // first step after the clip ended: the 12 maxima
                 const int fpar = fin_seq & 1;
                 WLM_TRC(fin_seq, 1);
@@ -817,7 +837,23 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
 #ifdef WLM_KO_MEL
             const float m1 = P[lane] + static_cast<float>(tcol & 1);
 #else
-            const float m1 = NMELS == 0 ? mel_stage(kt, P, wg, lane, tcol) : mel_fixed<NMELS == 0 ? 80 : NMELS>(kt, P, wg, lane, tcol);
+            float m1;
+            if constexpr (FLAT) {
+                // no retention: (max(log10 p, -10) + 4) / 4 goes to HBM now, the max - 8 clamp follows when the clip is done
+                const int nf = kt.nf[wg];
+                float* of = a.out + (static_cast<int64_t>(pb) * a.n_mels + kt.m0[wg]) * kNFrames + ptile * kTile + lane;
+                const bool va = ptile * kTile + lane < kNFrames;
+                auto sink = [&](const float (&o)[kMaxFiltersPerWarp]) {
+                    constexpr float kLog10_2 = 0.30102999566398120f;
+#pragma unroll
+                    for (int q = 0; q < kMaxFiltersPerWarp; ++q)
+                        if (q < nf && va) of[q * kNFrames] = fmaf(fmaxf(lg2_approx(o[q]) * kLog10_2, -10.0f), 0.25f, 1.0f);
+                };
+                m1 = NMELS == 0 ? mel_stage(kt, P, wg, lane, sink) : mel_fixed<NMELS == 0 ? 80 : NMELS>(kt, P, wg, lane, sink);
+            } else {
+                auto sink = [&](const float (&o)[kMaxFiltersPerWarp]) { tmem_st_x16(tcol, o); };
+                m1 = NMELS == 0 ? mel_stage(kt, P, wg, lane, sink) : mel_fixed<NMELS == 0 ? 80 : NMELS>(kt, P, wg, lane, sink);
+            }
 #endif
             if (ptile * kTile + lane < kNFrames) mx = fmaxf(mx, m1);     // frames past 3000 do not exist
             if (clip_ends) {
@@ -833,7 +869,39 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
         // ---- D: the clip ended: warp max -> group max; the LAST warp of the group to get here delivers the group's
         // max to all 6 CTAs (remote store + remote mbarrier arrive).  Nobody waits; the peers get a whole step of
         // slack before anyone needs the result (F, next step).
-        if (clip_ends) {
+        if (FLAT && clip_ends) {
+            // The CTA's 16 warps meet (once per clip), take the clip's max and clamp the clip's features in place:
+            // they were written moments ago and come back from L2.  flat_max is a ring of three so that the slot of the
+            // clip after next can be cleared here without racing with anybody (its last readers arrived above, its next
+            // writers wait for this thread's next arrival).
+            const int slot3 = clip_seq % 3;
+            __threadfence();                                         // this lane's feature stores are visible device-wide
+            __syncwarp();
+            if (lane == 0) {
+                if (mel_tile) atomicMax(flat_max + slot3, __float_as_int(wmax));
+                mbar_arrive(bar_clip);
+            }
+            mbar_wait(bar_clip, clip_seq & 1);
+            const float gmax = log10_floor(__int_as_float(*reinterpret_cast<volatile int*>(flat_max + slot3)));   // TF-FE:157
+            const float thr = (fmaxf(gmax - 8.0f, -10.0f) + 4.0f) * 0.25f;                                        // TF-FE:158,161
+            if (tid == 0) {
+                flat_max[(clip_seq + 2) % 3] = 0;
+                if (a.gmax) a.gmax[pb] = gmax;
+            }
+            const int n_valid = min(kNFrames, pn_act * kTile);          // frames of half-tiles that hold real samples
+            float4* oc = reinterpret_cast<float4*>(a.out + static_cast<int64_t>(pb) * a.n_mels * kNFrames);
+            for (int i = tid; i < a.n_mels * (kNFrames / 4); i += kThreads) {
+                const int f = (i % (kNFrames / 4)) * 4;
+                float4 v = make_float4(thr, thr, thr, thr);             // silent half-tiles: exactly -10 everywhere -> thr
+                if (f < n_valid) {                                      // (n_valid is a multiple of 4 or 3000)
+                    v = __ldcg(oc + i);
+                    v.x = fmaxf(v.x, thr); v.y = fmaxf(v.y, thr); v.z = fmaxf(v.z, thr); v.w = fmaxf(v.w, thr);
+                }
+                oc[i] = v;
+            }
+            ++clip_seq;
+        }
+        if (!FLAT && clip_ends) {
             while (pend) {      // (only when this clip had fewer half-tiles than the one before it: finish that one first)
                 if (out_j < pend_n_my) output_slot(out_j++);
                 if (out_j >= pend_n_my) pend = false;
@@ -884,7 +952,7 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
         // this step becomes the previous one; advance to the next step of the stream
         const int steps = cn_my > 0 ? cn_my : 1;
         pvalid = cvalid; phas = do_tile; plast = cvalid && cj + 1 >= steps;
-        pb = cb; pj = cj; ptile = ctile; pn_my = cn_my;
+        pb = cb; pj = cj; ptile = ctile; pn_my = cn_my; pn_act = cc.n_act;
         prev_tnum = tnum;
         if (do_tile) ++tnum;
         if (cvalid) {
@@ -902,19 +970,26 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
             }
         }
     }
-    // all TMEM reads are complete (tcgen05.wait::ld inside tmem_ld_x16); release the allocation
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    cluster.sync();   // also keeps every CTA's shared memory alive until its peers have delivered their last max
-    if (warp == 0) tmem_dealloc_512(tmem_base);
+    if constexpr (!FLAT) {
+        // all TMEM reads are complete (tcgen05.wait::ld inside tmem_ld_x16); release the allocation
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        cluster.sync();   // also keeps every CTA's shared memory alive until its peers have delivered their last max
+        if (warp == 0) tmem_dealloc_512(tmem_base);
+    }
 }
 
 // ---- host side -----------------------------------------------------------------------------------
 // variant: 80 / 128 when the table's structure equals the baked one (and the partition was taken from it)
 typedef void (*KernelFn)(const ClipArgs, const KernelTables, const float*);
-inline KernelFn kernel_for(int variant) {
-    if (variant == 80) return logmel_cluster_kernel<80>;
-    if (variant == 128) return logmel_cluster_kernel<128>;
-    return logmel_cluster_kernel<0>;
+inline KernelFn kernel_for(int variant, bool flat = false) {
+    if (flat) {
+        if (variant == 80) return logmel_cluster_kernel<80, true>;
+        if (variant == 128) return logmel_cluster_kernel<128, true>;
+        return logmel_cluster_kernel<0, true>;
+    }
+    if (variant == 80) return logmel_cluster_kernel<80, false>;
+    if (variant == 128) return logmel_cluster_kernel<128, false>;
+    return logmel_cluster_kernel<0, false>;
 }
 
 inline void fill_launch_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* at, int n_clusters, cudaStream_t st) {
@@ -935,6 +1010,8 @@ inline cudaError_t configure(int variant, int* max_clusters) {
     KernelFn fn = kernel_for(variant);
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(kernel_for(variant, true), cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg;
     cudaLaunchAttribute at[1];
     fill_launch_config(&cfg, at, 148, nullptr);
@@ -946,14 +1023,55 @@ inline cudaError_t configure(int variant, int* max_clusters) {
     return cudaSuccess;
 }
 
+// How many clips go to the flat kernel on the `flat_ctas` SMs the clusters leave idle: the largest number of whole rounds
+// (one clip per flat CTA) that finish no later than the cluster kernel does with the rest.  Next to a running cluster kernel
+// a flat CTA needs 214 us (80 mels) / 253 us (128 mels) per 30 s clip against 29.5 / 30.3 us per cluster round
+// (tools/flat_time.py): 7.3 / 8.4 rounds, taken with a margin.  The ratio barely depends on the clip length as long as all
+// clips have the SAME length, which is the only case the split is used for: with per-clip lengths the last clips of a batch
+// could be the long ones, and a static split would leave the whole GPU waiting for 16 SMs.
+inline int flat_clip_count(const ClipArgs& a, int max_clusters, int flat_ctas) {
+    if (flat_ctas <= 0 || a.lengths != nullptr || a.B < 2 * max_clusters) return 0;
+    const double rounds_per_clip = 5.2 + 0.0285 * a.n_mels;
+    int k = 0;
+    while ((k + 1) * flat_ctas < a.B &&
+           (k + 1) * rounds_per_clip <= (a.B - (k + 1) * flat_ctas + max_clusters - 1) / max_clusters) ++k;
+    return k * flat_ctas;
+}
+
+// Clips [0, B - n_flat) go to the cluster kernel, the last n_flat to the flat kernel, both on `st`.  The flat kernel is a
+// PROGRAMMATIC DEPENDENT launch: it becomes schedulable when every CTA of the cluster kernel has executed
+// griddepcontrol.launch_dependents, i.e. is resident -- its CTAs can then only land on the SMs the clusters left free.
+// (Submitted as an independent kernel on a second stream it sometimes got SMs first and kept clusters from being placed.)
+// It consumes nothing the cluster kernel produces, so it never waits for it; later work in the stream waits for both.
 inline cudaError_t launch(const ClipArgs& a, const Tables* d_tables, const Tables& h_tables, int variant,
-                          int max_clusters, cudaStream_t st, int* n_launches) {
-    const int n_clusters = a.B < max_clusters ? a.B : max_clusters;
+                          int max_clusters, cudaStream_t st, int* n_launches, int flat_ctas = 0) {
+    int n_flat = flat_clip_count(a, max_clusters, flat_ctas);
+    if (const char* e = getenv("WLM_FLAT_CLIPS")) n_flat = (flat_ctas > 0 && atoi(e) < a.B) ? atoi(e) : 0;
+    ClipArgs ac = a;
+    ac.clip_first = 0;
+    ac.B = a.B - n_flat;
+    const int n_clusters = ac.B < max_clusters ? ac.B : max_clusters;
     cudaLaunchConfig_t cfg;
     cudaLaunchAttribute at[1];
     fill_launch_config(&cfg, at, n_clusters, st);
     *n_launches = 1;
-    return cudaLaunchKernelEx(&cfg, kernel_for(variant), a, h_tables.mel, static_cast<const float*>(d_tables->win_lane));
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel_for(variant), ac, h_tables.mel, static_cast<const float*>(d_tables->win_lane));
+    if (e != cudaSuccess || n_flat == 0) return e;
+    ClipArgs af = a;
+    af.clip_first = a.B - n_flat;
+    cudaLaunchConfig_t fcfg;
+    memset(&fcfg, 0, sizeof(fcfg));
+    fcfg.gridDim = dim3(n_flat < flat_ctas ? n_flat : flat_ctas);
+    fcfg.blockDim = dim3(kThreads);
+    fcfg.dynamicSmemBytes = kSmemBytes;
+    fcfg.stream = st;
+    cudaLaunchAttribute fat[1];
+    fat[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    fat[0].val.programmaticStreamSerializationAllowed = 1;
+    fcfg.attrs = fat;
+    fcfg.numAttrs = 1;
+    *n_launches = 2;
+    return cudaLaunchKernelEx(&fcfg, kernel_for(variant, true), af, h_tables.mel, static_cast<const float*>(d_tables->win_lane));
 }
 
 }  // namespace fused

@@ -70,6 +70,7 @@ struct wlm_plan {
     fused::Tables h_fused_tables;
 #endif
     int max_clusters = 0;          // co-resident clusters of the fused kernel (occupancy query)
+    int flat_ctas = 0;             // SMs the clusters cannot cover: they run the flat kernel (programmatic dependent launch)
     int variant = 0;               // 80 / 128: unrolled mel stage (Whisper banks); 0: table-driven
 
     // wlm_logmel_host pipeline
@@ -215,6 +216,9 @@ extern "C" int wlm_plan_create(int device, int n_mels, const float* mel_dense_ho
             wlm_plan_destroy(p);
             return fail(WLM_ERR_CUDA, "fused kernel configuration failed: %s", cudaGetErrorString(fe));
         }
+        // the SMs that whole clusters cannot cover run the flat kernel (WLM_FLAT=0 turns that off)
+        const char* fl = getenv("WLM_FLAT");
+        p->flat_ctas = (fl && atoi(fl) == 0) ? 0 : std::max(0, p->sm_count - fused::kCluster * p->max_clusters);
     }
 #endif
 
@@ -276,7 +280,8 @@ static int launch_logmel(wlm_plan* p, const ClipArgs& a, cudaStream_t st) {
 #ifdef WLM_HAVE_FUSED
     else {
         int n_launches = 0;
-        cudaError_t e = fused::launch(a, p->d_fused_tables, p->h_fused_tables, p->variant, p->max_clusters, st, &n_launches);
+        cudaError_t e = fused::launch(a, p->d_fused_tables, p->h_fused_tables, p->variant, p->max_clusters, st, &n_launches,
+                                      p->flat_ctas);
         if (e != cudaSuccess) return fail(WLM_ERR_CUDA, "fused launch failed: %s", cudaGetErrorString(e));
         p->launches += n_launches;
     }
@@ -320,6 +325,7 @@ extern "C" int wlm_logmel(wlm_plan* p, const void* pcm_dev, int pcm_format, cons
     a.pcm_format = pcm_format;
     a.n_mels = p->n_mels;
     a.B = B;
+    a.clip_first = 0;
     a.out = out_dev;
     a.gmax = gmax;
     return launch_logmel(p, a, static_cast<cudaStream_t>(stream));
@@ -486,6 +492,7 @@ extern "C" int wlm_logmel_host(wlm_plan* p, const void* const* clips_host, const
         a.pcm_format = pcm_format;
         a.n_mels = p->n_mels;
         a.B = b1 - b0;
+        a.clip_first = 0;
         a.out = out_dev + (size_t)b0 * p->n_mels * kNFrames;
         a.gmax = static_cast<float*>(p->d_ws) + b0;
         int rc = launch_logmel(p, a, st);

@@ -34,7 +34,8 @@ struct ClipArgs {
     int32_t dense_len;        // min(row_stride, 480000) when lengths == nullptr
     int32_t pcm_format;       // WLM_PCM_*
     int32_t n_mels;
-    int32_t B;
+    int32_t B;                // clips [clip_first, B) are processed by this launch
+    int32_t clip_first;
     float* out;               // [B][n_mels][3000]
     float* gmax;              // [B] (may be workspace)
 };
