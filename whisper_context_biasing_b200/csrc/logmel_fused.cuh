@@ -890,14 +890,22 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
             }
             const int n_valid = min(kNFrames, pn_act * kTile);          // frames of half-tiles that hold real samples
             float4* oc = reinterpret_cast<float4*>(a.out + static_cast<int64_t>(pb) * a.n_mels * kNFrames);
-            for (int i = tid; i < a.n_mels * (kNFrames / 4); i += kThreads) {
-                const int f = (i % (kNFrames / 4)) * 4;
-                float4 v = make_float4(thr, thr, thr, thr);             // silent half-tiles: exactly -10 everywhere -> thr
-                if (f < n_valid) {                                      // (n_valid is a multiple of 4 or 3000)
-                    v = __ldcg(oc + i);
-                    v.x = fmaxf(v.x, thr); v.y = fmaxf(v.y, thr); v.z = fmaxf(v.z, thr); v.w = fmaxf(v.w, thr);
+            // eight 16-byte loads in flight per thread: the clip may have left L2 by now (the cluster kernel streams through it)
+            const int n4 = a.n_mels * (kNFrames / 4);
+            for (int i0 = tid; i0 < n4; i0 += 8 * kThreads) {
+                float4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int i = i0 + u * kThreads;
+                    v[u] = make_float4(thr, thr, thr, thr);             // silent half-tiles: exactly -10 everywhere -> thr
+                    if (i < n4 && (i % (kNFrames / 4)) * 4 < n_valid) v[u] = __ldcg(oc + i);    // (n_valid: multiple of 4 or 3000)
                 }
-                oc[i] = v;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int i = i0 + u * kThreads;
+                    v[u].x = fmaxf(v[u].x, thr); v[u].y = fmaxf(v[u].y, thr); v[u].z = fmaxf(v[u].z, thr); v[u].w = fmaxf(v[u].w, thr);
+                    if (i < n4) oc[i] = v[u];
+                }
             }
             ++clip_seq;
         }
@@ -1025,13 +1033,13 @@ inline cudaError_t configure(int variant, int* max_clusters) {
 
 // How many clips go to the flat kernel on the `flat_ctas` SMs the clusters leave idle: the largest number of whole rounds
 // (one clip per flat CTA) that finish no later than the cluster kernel does with the rest.  Next to a running cluster kernel
-// a flat CTA needs 214 us (80 mels) / 253 us (128 mels) per 30 s clip against 29.5 / 30.3 us per cluster round
-// (tools/flat_time.py): 7.3 / 8.4 rounds, taken with a margin.  The ratio barely depends on the clip length as long as all
+// a flat CTA needs about 205 us (80 mels) / 215 us (128 mels) per 30 s clip against 29.5 / 30.3 us per cluster round
+// (tools/flat_time.py): 7.0 / 7.3 rounds.  The ratio barely depends on the clip length as long as all
 // clips have the SAME length, which is the only case the split is used for: with per-clip lengths the last clips of a batch
 // could be the long ones, and a static split would leave the whole GPU waiting for 16 SMs.
 inline int flat_clip_count(const ClipArgs& a, int max_clusters, int flat_ctas) {
     if (flat_ctas <= 0 || a.lengths != nullptr || a.B < 2 * max_clusters) return 0;
-    const double rounds_per_clip = 5.2 + 0.0285 * a.n_mels;
+    const double rounds_per_clip = 6.5 + 0.00625 * a.n_mels;
     int k = 0;
     while ((k + 1) * flat_ctas < a.B &&
            (k + 1) * rounds_per_clip <= (a.B - (k + 1) * flat_ctas + max_clusters - 1) / max_clusters) ++k;
