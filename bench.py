@@ -379,18 +379,20 @@ def run_ours(args, wl, rank, world, local_rank):
         dist.destroy_process_group()
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of the fused kernel per clip, from the `ncu --set full`
-# captures summarised under profiles/ (r01c_c2_80mel_summary.txt: 491.58 + 205.57 MB for 256 clips;
-# r01c_c3_128mel_summary.txt: 1966.21 + 1520.97 MB for 1024 clips).  Algorithmic: 2.88 / 3.456 MB per clip;
-# the measured traffic is slightly lower because the tail of the output is still dirty in L2 at kernel end.
-KERNEL_DRAM_TRAFFIC_PER_CLIP = {80: 697151232 / 256, 128: 3487177000 / 1024}
+# dram__bytes_read.sum + dram__bytes_write.sum per clip, summed over the TWO kernels of a step (cluster kernel + the flat
+# kernel that runs under it on the 16 SMs the clusters cannot cover), from the `ncu --set full` captures summarised under
+# profiles/ (r01d_c2_80mel_summary.txt: 461.06 + 189.44 + 30.79 + 0.06 MB for 256 clips; r01d_c3_128mel_summary.txt:
+# 1813.79 + 1399.15 + 153.70 + 82.48 MB for 1024 clips).  Algorithmic: 2.88 / 3.456 MB per clip; the measured traffic is
+# slightly lower because the tail of the output is still dirty in L2 at kernel end (ncu runs the two kernels one after the
+# other, so the flat kernel's clamp pass finds its clip in L2 there).
+KERNEL_DRAM_TRAFFIC_PER_CLIP = {80: 681350000 / 256, 128: 3449120000 / 1024}
 
 # FP32 side of the roofline (SURVEY 8d convention: 32.49 / 33.23 MFLOP per 30 s clip; nominal CUDA-core peak =
 # 148 SMs x 128 lanes x 2 flop x SM clock).  The pipe utilisations are the ncu counters of the same captures
 # (sm__pipe_fma_cycles_active, l1tex__data_pipe_lsu_wavefronts_mem_shared, smsp__issue_active: % of peak while active).
 ALGORITHMIC_MFLOP_PER_CLIP = {80: 32.49, 128: 33.23}
-NCU_PIPE_PCT = {80: {"fma_pipe": 51.8, "shared_memory_wavefronts": 48.2, "issue_slots": 61.1},
-                128: {"fma_pipe": 50.6, "shared_memory_wavefronts": 47.3, "issue_slots": 61.0}}
+NCU_PIPE_PCT = {80: {"fma_pipe": 51.6, "shared_memory_wavefronts": 48.1, "issue_slots": 61.2},
+                128: {"fma_pipe": 50.2, "shared_memory_wavefronts": 47.2, "issue_slots": 61.0}}
 
 
 def cpu_baseline(n_mels):
