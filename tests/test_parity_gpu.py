@@ -365,3 +365,39 @@ def test_feature_cache_over_the_extractor(fe):
     half = FeatureCache(ex, capacity_bytes=16 * 80 * 3000 * 2, dtype=torch.float16)
     h = half.get_many(order, load)
     assert (h - direct).abs().max().item() <= 1e-3          # fp16 storage of values in [-1.5, 1.5]
+
+
+def test_flat_kernel_matches_cluster_kernel(fe, monkeypatch):
+    """The cluster-less twin of the kernel (it runs on the SMs that whole clusters cannot cover, as a programmatic dependent
+    launch; dense batches only by default) must give bit-identical features and per-clip maxima: same FFT, same mel sums,
+    and its in-place clamp pass equals the cluster kernel's clamp-then-scale."""
+    import torch
+
+    g = torch.Generator(device="cpu").manual_seed(5)
+    for m in (80, 128):
+        ex = fe[m]
+        pcm = (0.1 * torch.randn(50, 480000, generator=g)).to(ex.device)
+        pcm[3] = 0.0
+        pcm[4, 200000:] = 0.0
+        monkeypatch.setenv("WLM_FLAT_CLIPS", "0")
+        n0 = ex.launch_count
+        ref, ref_gmax = ex.extract_device(pcm, return_gmax=True)
+        assert ex.launch_count == n0 + 1
+        monkeypatch.setenv("WLM_FLAT_CLIPS", "20")          # the last 20 clips: 16 flat CTAs, four of them take two clips
+        got, got_gmax = ex.extract_device(pcm, return_gmax=True)
+        assert ex.launch_count == n0 + 3                    # cluster kernel + flat kernel
+        assert torch.equal(got, ref) and torch.equal(got_gmax, ref_gmax)
+        # ragged lengths (the library never splits those on its own: the override does)
+        lens = torch.tensor([0, 1, 5000, 5121, 100000, 479999, 480000] * 5, dtype=torch.int32, device=ex.device)
+        monkeypatch.setenv("WLM_FLAT_CLIPS", "0")
+        ref = ex.extract_device(pcm[:35], lengths=lens)
+        monkeypatch.setenv("WLM_FLAT_CLIPS", "17")
+        got = ex.extract_device(pcm[:35], lengths=lens)
+        assert torch.equal(got, ref)
+    monkeypatch.delenv("WLM_FLAT_CLIPS")
+    # the library's own split: a dense batch of 256 goes out as two kernels
+    ex = fe[80]
+    pcm = (0.1 * torch.randn(256, 480000, generator=g)).to(ex.device)
+    n0 = ex.launch_count
+    ex.extract_device(pcm)
+    assert ex.launch_count == n0 + (2 if ex.sm_count > 6 * ex.max_clusters else 1)

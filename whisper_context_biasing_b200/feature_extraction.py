@@ -166,6 +166,11 @@ class B200WhisperFeatureExtractor:
     def max_clusters(self) -> int:
         return int(N.LIB.wlm_plan_max_clusters(self._plan))
 
+    @property
+    def sm_count(self) -> int:
+        """SMs of the device; `sm_count - 6 * max_clusters` of them run the cluster-less twin of the kernel."""
+        return int(N.LIB.wlm_plan_sm_count(self._plan))
+
     # -- helpers -----------------------------------------------------------------------------
     def _stream(self):
         import torch
