@@ -1052,7 +1052,7 @@ inline int flat_clip_count(const ClipArgs& a, int max_clusters, int flat_ctas) {
 // (Submitted as an independent kernel on a second stream it sometimes got SMs first and kept clusters from being placed.)
 // It consumes nothing the cluster kernel produces, so it never waits for it; later work in the stream waits for both.
 inline cudaError_t launch(const ClipArgs& a, const Tables* d_tables, const Tables& h_tables, int variant,
-                          int max_clusters, cudaStream_t st, int* n_launches, int flat_ctas = 0) {
+                          int max_clusters, cudaStream_t st, int* n_launches, int flat_ctas = 0, bool* flat_broken = nullptr) {
     int n_flat = flat_clip_count(a, max_clusters, flat_ctas);
     if (const char* e = getenv("WLM_FLAT_CLIPS")) n_flat = (flat_ctas > 0 && atoi(e) < a.B) ? atoi(e) : 0;
     ClipArgs ac = a;
@@ -1079,7 +1079,15 @@ inline cudaError_t launch(const ClipArgs& a, const Tables* d_tables, const Table
     fcfg.attrs = fat;
     fcfg.numAttrs = 1;
     *n_launches = 2;
-    return cudaLaunchKernelEx(&fcfg, kernel_for(variant, true), af, h_tables.mel, static_cast<const float*>(d_tables->win_lane));
+    e = cudaLaunchKernelEx(&fcfg, kernel_for(variant, true), af, h_tables.mel, static_cast<const float*>(d_tables->win_lane));
+    if (e == cudaSuccess) return e;
+    // the dependent launch was refused (driver without programmatic launches?): the cluster kernel takes the remaining
+    // clips in a second, ordinary launch, and the plan stops splitting
+    (void)cudaGetLastError();
+    if (flat_broken) *flat_broken = true;
+    const int n2 = n_flat < max_clusters ? n_flat : max_clusters;
+    fill_launch_config(&cfg, at, n2, st);
+    return cudaLaunchKernelEx(&cfg, kernel_for(variant), af, h_tables.mel, static_cast<const float*>(d_tables->win_lane));
 }
 
 }  // namespace fused

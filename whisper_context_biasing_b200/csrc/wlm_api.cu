@@ -280,8 +280,10 @@ static int launch_logmel(wlm_plan* p, const ClipArgs& a, cudaStream_t st) {
 #ifdef WLM_HAVE_FUSED
     else {
         int n_launches = 0;
+        bool flat_broken = false;
         cudaError_t e = fused::launch(a, p->d_fused_tables, p->h_fused_tables, p->variant, p->max_clusters, st, &n_launches,
-                                      p->flat_ctas);
+                                      p->flat_ctas, &flat_broken);
+        if (flat_broken) p->flat_ctas = 0;
         if (e != cudaSuccess) return fail(WLM_ERR_CUDA, "fused launch failed: %s", cudaGetErrorString(e));
         p->launches += n_launches;
     }
