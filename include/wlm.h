@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define WLM_VERSION 10000 /* 1.00.00 */
+#define WLM_VERSION 10100 /* 1.01.00 */
 
 #define WLM_SAMPLING_RATE 16000 /* TF-FE:72 */
 #define WLM_N_FFT 400           /* TF-FE:75 */
@@ -60,9 +60,14 @@ enum {
     WLM_PCM_I16 = 1  /* int16; converted on the GPU as x/32768 (data_loader.py:48 load_wave) */
 };
 
-/* Output element formats. */
+/* Output element formats (wlm_plan_set_output_format).  Layout is always [B, n_mels, 3000],
+ * mel-major, frame-contiguous.  The 16-bit formats are the round-to-nearest of the float32 value:
+ * the model of the reference runs under fp16 autocast (REF/scripts/train.py:250), so its first
+ * convolution rounds the features to 16 bits anyway; storing them that way halves the write bytes. */
 enum {
-    WLM_OUT_F32 = 0 /* float32 [B, n_mels, 3000], mel-major, frame-contiguous (TF-FE:326) */
+    WLM_OUT_F32 = 0, /* float32: what the reference returns (TF-FE:326) */
+    WLM_OUT_BF16 = 1,
+    WLM_OUT_F16 = 2
 };
 
 typedef struct wlm_plan wlm_plan;
@@ -99,6 +104,22 @@ int wlm_plan_kernel_variant(const wlm_plan* plan);
 int wlm_plan_max_clusters(const wlm_plan* plan);
 
 /*
+ * Element type of `out_dev` for every later wlm_logmel / wlm_logmel_host call of this plan
+ * (default WLM_OUT_F32).  With a 16-bit format `out_dev` points to 2-byte elements and
+ * `out_host` of wlm_logmel_host likewise.
+ */
+int wlm_plan_set_output_format(wlm_plan* plan, int out_format);
+int wlm_plan_output_format(const wlm_plan* plan);
+
+/*
+ * Debug / measurement knob: how many clips of a DENSE batch (no lengths) go to the cluster-less
+ * twin of the kernel that runs on the SMs whole clusters cannot cover.  -1 (default) = the
+ * library's own split.  The environment variable WLM_FLAT_CLIPS, read ONCE when the plan is
+ * created, sets the initial value.  Values are clamped to [0, B - 1] at launch.
+ */
+int wlm_plan_set_flat_clips(wlm_plan* plan, int n_flat);
+
+/*
  * Device scratch needed by wlm_logmel for a batch of B clips (bytes, 256-aligned).
  * May be 0.  The buffer is only used during the call's stream work.
  */
@@ -127,14 +148,15 @@ size_t wlm_workspace_bytes(const wlm_plan* plan, int B);
  *                 else  -> device int32[B], valid samples of clip b (any value >= 0; values
  *                          above 480000 are truncated, the rest is right-padded with zeros,
  *                          exactly as TF-SU:327-332 and :268-278 do on the host).
- *   out_dev       device float32 [B][n_mels][3000], 16-byte aligned.
+ *   out_dev       device [B][n_mels][3000] of the plan's output format (float32 unless
+ *                 wlm_plan_set_output_format was called), 16-byte aligned.
  *   gmax_dev      optional device float32[B]: receives the per-clip max of log10(mel)
  *                 (the value TF-FE:157 computes); may be NULL.
  *   workspace     device scratch of at least wlm_workspace_bytes(plan,B) bytes (or NULL if 0).
  *   stream        cudaStream_t (as void*) the work is enqueued on.
  */
 int wlm_logmel(wlm_plan* plan, const void* pcm_dev, int pcm_format, const int64_t* offsets_dev,
-               const int32_t* lengths_dev, int64_t row_stride, int B, float* out_dev,
+               const int32_t* lengths_dev, int64_t row_stride, int B, void* out_dev,
                float* gmax_dev, void* workspace, size_t workspace_bytes, void* stream);
 
 /*
@@ -154,11 +176,11 @@ int wlm_frame_mask(wlm_plan* plan, const int32_t* lengths_dev, int B, int32_t* m
  *
  *   clips_host    array of B host pointers (element type pcm_format), lengths_host[b] valid
  *                 samples each (any value >= 0; >480000 is truncated).
- *   out_host      optional host float32 [B][n_mels][3000]: if not NULL the features are also
+ *   out_host      optional host [B][n_mels][3000] (same element type as out_dev): if not NULL the features are also
  *                 copied back (D2H inside the call, which then blocks until they arrived).
  */
 int wlm_logmel_host(wlm_plan* plan, const void* const* clips_host, const int32_t* lengths_host,
-                    int pcm_format, int B, float* out_dev, float* out_host, void* stream);
+                    int pcm_format, int B, void* out_dev, void* out_host, void* stream);
 
 /* Number of kernels the plan has launched so far (bench.py's gpu_launches evidence). */
 int64_t wlm_plan_launch_count(const wlm_plan* plan);

@@ -112,13 +112,13 @@ class _EpochBatches:
 
 
 def time_reference_dataloader(clips, n_mels: int, batch_size: int = 16, num_workers: int | None = None,
-                              path: str = "default"):
-    """Returns dict(audio_s_per_s, seconds, clips, cores).  Audio-seconds are NOMINAL 30 s
+                              path: str = "default", epochs: int = 1, warmup_epochs: int = 1):
+    """Returns dict(audio_s_per_s, seconds, epoch_seconds, clips, cores).  Audio-seconds are NOMINAL 30 s
     windows per clip (the extractor always pads/trims to 30 s).
 
-    Persistent workers; an untimed short epoch (two batches per worker) pays for worker start-up
-    and extractor construction, then one full epoch is timed from the creation of its iterator,
-    so prefetching cannot hide work from the clock."""
+    ONE DataLoader with persistent workers for the whole measurement: `warmup_epochs` untimed short epochs (two batches
+    per worker) pay for worker start-up and extractor construction, then `epochs` full epochs are timed, each from the
+    creation of its iterator, so prefetching cannot hide work from the clock.  `clips` in the result is per epoch."""
     from torch.utils.data import DataLoader
 
     if num_workers is None:
@@ -128,14 +128,19 @@ def time_reference_dataloader(clips, n_mels: int, batch_size: int = 16, num_work
                     collate_fn=_RefStyleCollate(n_mels), persistent_workers=num_workers > 0,
                     prefetch_factor=2 if num_workers > 0 else None)
     sampler.limit = 2 * batch_size * max(1, num_workers)
-    for _ in dl:
-        pass
+    for _ in range(max(1, warmup_epochs)):
+        for _ in dl:
+            pass
     sampler.limit = None
-    t0 = time.perf_counter()
+    secs = []
     n_timed = 0
-    for b in dl:
-        n_timed += b["input_features"].shape[0]
-    dt = time.perf_counter() - t0
+    for _ in range(max(1, epochs)):
+        t0 = time.perf_counter()
+        n_timed = 0
+        for b in dl:
+            n_timed += b["input_features"].shape[0]
+        secs.append(time.perf_counter() - t0)
     del dl
-    return {"audio_s_per_s": 30.0 * n_timed / dt if dt > 0 else 0.0, "seconds": dt,
-            "clips": n_timed, "cores": max(1, num_workers)}
+    total = sum(secs)
+    return {"audio_s_per_s": 30.0 * n_timed * len(secs) / total if total > 0 else 0.0, "seconds": total,
+            "epoch_seconds": secs, "clips": n_timed, "cores": max(1, num_workers)}

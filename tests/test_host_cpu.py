@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     raw = C.CDLL(N.lib_path())
     for name in declared:
         assert getattr(raw, name) is not None
-    assert N.LIB.wlm_version() == 10000
+    assert N.LIB.wlm_version() == 10100
 
 
 def test_mel_table_bit_identical_to_reference(golden):

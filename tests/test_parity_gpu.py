@@ -367,7 +367,7 @@ def test_feature_cache_over_the_extractor(fe):
     assert (h - direct).abs().max().item() <= 1e-3          # fp16 storage of values in [-1.5, 1.5]
 
 
-def test_flat_kernel_matches_cluster_kernel(fe, monkeypatch):
+def test_flat_kernel_matches_cluster_kernel(fe):
     """The cluster-less twin of the kernel (it runs on the SMs that whole clusters cannot cover, as a programmatic dependent
     launch; dense batches only by default) must give bit-identical features and per-clip maxima: same FFT, same mel sums,
     and its in-place clamp pass equals the cluster kernel's clamp-then-scale."""
@@ -379,25 +379,170 @@ def test_flat_kernel_matches_cluster_kernel(fe, monkeypatch):
         pcm = (0.1 * torch.randn(50, 480000, generator=g)).to(ex.device)
         pcm[3] = 0.0
         pcm[4, 200000:] = 0.0
-        monkeypatch.setenv("WLM_FLAT_CLIPS", "0")
+        ex.set_flat_clips(0)
         n0 = ex.launch_count
         ref, ref_gmax = ex.extract_device(pcm, return_gmax=True)
         assert ex.launch_count == n0 + 1
-        monkeypatch.setenv("WLM_FLAT_CLIPS", "20")          # the last 20 clips: 16 flat CTAs, four of them take two clips
+        ex.set_flat_clips(20)          # the last 20 clips: 16 flat CTAs, four of them take two clips
         got, got_gmax = ex.extract_device(pcm, return_gmax=True)
         assert ex.launch_count == n0 + 3                    # cluster kernel + flat kernel
         assert torch.equal(got, ref) and torch.equal(got_gmax, ref_gmax)
         # ragged lengths (the library never splits those on its own: the override does)
         lens = torch.tensor([0, 1, 5000, 5121, 100000, 479999, 480000] * 5, dtype=torch.int32, device=ex.device)
-        monkeypatch.setenv("WLM_FLAT_CLIPS", "0")
+        ex.set_flat_clips(0)
         ref = ex.extract_device(pcm[:35], lengths=lens)
-        monkeypatch.setenv("WLM_FLAT_CLIPS", "17")
+        ex.set_flat_clips(17)
         got = ex.extract_device(pcm[:35], lengths=lens)
         assert torch.equal(got, ref)
-    monkeypatch.delenv("WLM_FLAT_CLIPS")
+        ex.set_flat_clips(-1)
     # the library's own split: a dense batch of 256 goes out as two kernels
     ex = fe[80]
     pcm = (0.1 * torch.randn(256, 480000, generator=g)).to(ex.device)
     n0 = ex.launch_count
     ex.extract_device(pcm)
     assert ex.launch_count == n0 + (2 if ex.sm_count > 6 * ex.max_clusters else 1)
+
+
+def test_flat_kernel_small_share_read_back_at_once(fe):
+    """The flat kernel is a programmatic dependent of the cluster kernel and finishes long before it when its share is
+    small; it executes griddepcontrol.wait before exiting, so work queued behind the pair (here: the D2H copy of the
+    features) must see what BOTH kernels wrote."""
+    import torch
+
+    ex = fe[80]
+    g = torch.Generator(device="cpu").manual_seed(9)
+    base = (0.1 * torch.randn(64, 480000, generator=g)).to(ex.device)
+    pcm = base.repeat(8, 1)                                  # 512 clips
+    ex.set_flat_clips(0)
+    ref = ex.extract_device(pcm[:64]).cpu()
+    ex.set_flat_clips(16)
+    host = torch.empty((512, 80, 3000), dtype=torch.float32).pin_memory()
+    for _ in range(3):
+        out = ex.extract_device(pcm)
+        host.copy_(out, non_blocking=True)                   # queued right behind the two kernels
+        out.zero_()                                          # and the buffer is reused at once
+        torch.cuda.current_stream().synchronize()
+        for r in range(8):
+            assert torch.equal(host[64 * r:64 * (r + 1)], ref), r
+    ex.set_flat_clips(-1)
+
+
+@pytest.mark.parametrize("n_mels", [80, 128])
+def test_sixteen_bit_feature_store(n_mels):
+    """the kernel can store bfloat16 / float16 features (the model runs under fp16 autocast,
+    REF/scripts/train.py:250).  They must be the round-to-nearest of the float32 features, bit for bit, on the cluster
+    kernel and on its flat twin, for dense, ragged and host inputs; tolerance against the oracle: 16-bit rounding of
+    values in [-1.5, 2] (bf16: 2^-8 relative -> 7.9e-3 absolute worst case, fp16: 2^-11 -> 9.8e-4) on top of TOL."""
+    import torch
+
+    from whisper_context_biasing_b200 import B200WhisperFeatureExtractor
+
+    ex32 = B200WhisperFeatureExtractor(feature_size=n_mels)
+    g = torch.Generator(device="cpu").manual_seed(17)
+    pcm = (0.1 * torch.randn(40, 480000, generator=g)).to(ex32.device)
+    pcm[5] = 0.0
+    pcm[6, 100000:] = 0.0
+    lens = torch.tensor([0, 1, 5000, 5121, 100000, 479999, 480000, 33333] * 5, dtype=torch.int32, device=ex32.device)
+    ref_dense = ex32.extract_device(pcm)
+    ref_ragged = ex32.extract_device(pcm, lengths=lens)
+    clips = [O.synth_clip("speech", 48000, 1), O.synth_clip("noise", 480000, 2), O.synth_clip("zeros", 100, 3)]
+    oracle = O.extract(clips, n_mels, "f64")
+    for dt, tol in ((torch.bfloat16, 8e-3), (torch.float16, 1e-3)):
+        ex = B200WhisperFeatureExtractor(feature_size=n_mels, feature_dtype=dt)
+        for nflat in (0, 17):
+            ex.set_flat_clips(nflat)
+            got = ex.extract_device(pcm)
+            assert got.dtype == dt and torch.equal(got, ref_dense.to(dt)), (dt, nflat)
+            got = ex.extract_device(pcm, lengths=lens)
+            assert torch.equal(got, ref_ragged.to(dt)), (dt, nflat)
+        ex.set_flat_clips(-1)
+        h = ex(clips, sampling_rate=16000).input_features
+        assert h.dtype == dt
+        assert np.abs(h.float().cpu().numpy() - oracle).max() <= tol + TOL
+        ex.close()
+    ex32.close()
+
+
+def test_c3_full_size_128_mels(fe):
+    """BASELINE configs[2] at full size: 1024 x 30 s, 128 mels.  The library's own split between the cluster kernel and
+    its flat twin is bit-identical to the cluster kernel alone; every shard of G = 2, 4, 8 ranks is bit-identical to the
+    same clips of the single-GPU run; 64 clips sampled across the 8 shard ranges match the oracle."""
+    import torch
+
+    ex = fe[128]
+    B = 1024
+    g = torch.Generator(device="cpu").manual_seed(2)
+    base = 0.1 * torch.randn(128, 480000, generator=g)
+    pcm = torch.empty((B, 480000), dtype=torch.float32, device=ex.device)
+    for r in range(8):                                        # 8 x 128 clips, each block scaled differently
+        pcm[128 * r:128 * (r + 1)] = (base * (0.25 + 0.25 * r)).to(ex.device)
+    pcm[5] = 0.0
+    pcm[900, 123456:] = 0.0
+    ex.set_flat_clips(0)
+    n0 = ex.launch_count
+    alone = ex.extract_device(pcm)
+    assert ex.launch_count == n0 + 1
+    ex.set_flat_clips(-1)
+    full = ex.extract_device(pcm)
+    if ex.sm_count > 6 * ex.max_clusters:
+        assert ex.launch_count == n0 + 3                      # cluster kernel + flat kernel
+    assert torch.equal(full, alone)
+    del alone
+    for G in (2, 4, 8):
+        per = B // G
+        for r in range(G):
+            part = ex.extract_device(pcm[r * per:(r + 1) * per])
+            assert torch.equal(part, full[r * per:(r + 1) * per]), (G, r)
+    assert torch.all(full[5] == -1.5) and torch.isfinite(full).all()
+    idx = sorted({128 * r + o for r in range(8) for o in (0, 5, 17, 40, 63, 90, 111, 127)})
+    ref = O.log_mel_spectrogram(pcm[idx].cpu().numpy(), 128, "f64")
+    err = np.abs(full[idx].cpu().numpy() - ref).max()
+    assert err <= TOL, err
+
+
+def _shard_worker(rank, world, n_devices, n_clips, n_mels, seed, q):
+    import torch
+
+    from whisper_context_biasing_b200 import B200WhisperFeatureExtractor
+    from whisper_context_biasing_b200.sharding import clip_shard
+
+    dev = torch.device("cuda", rank % n_devices)
+    torch.cuda.set_device(dev)
+    lo, hi = clip_shard(n_clips, rank, world)
+    ex = B200WhisperFeatureExtractor(feature_size=n_mels, device=dev)
+    clips = [O.synth_clip(("noise", "speech", "chirp", "gap")[b % 4], 480000 if b % 3 else 100000 + 997 * b, seed + b)
+             for b in range(lo, hi)]
+    feats = ex(clips, sampling_rate=16000, return_tensors="np").input_features
+    q.put((rank, lo, hi, [_sha(f) for f in feats]))
+    ex.close()
+
+
+def test_multi_process_shards_match_single_process(fe):
+    """one process per GPU, clips sharded contiguously, no collective.  Spawns one process per visible GPU (two
+    processes on the one GPU of a single-GPU box), each extracting its clip_shard through the reference-facing call; the
+    per-clip sha256 must equal the single-process run's."""
+    import torch
+    import torch.multiprocessing as mp
+
+    n_dev = torch.cuda.device_count()
+    world = 2 if n_dev == 1 else min(n_dev, 8)
+    n_clips, n_mels, seed = 24, 80, 4000
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_shard_worker, args=(r, world, n_dev, n_clips, n_mels, seed, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = {}
+    for _ in range(world):
+        rank, lo, hi, shas = q.get(timeout=600)
+        for b, s in zip(range(lo, hi), shas):
+            got[b] = s
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    clips = [O.synth_clip(("noise", "speech", "chirp", "gap")[b % 4], 480000 if b % 3 else 100000 + 997 * b, seed + b)
+             for b in range(n_clips)]
+    ref = fe[80](clips, sampling_rate=16000, return_tensors="np").input_features
+    assert sorted(got) == list(range(n_clips))
+    for b in range(n_clips):
+        assert got[b] == _sha(ref[b]), b

@@ -1,4 +1,4 @@
-"""Launch time against the number of clips handed to the flat kernel (WLM_FLAT_CLIPS; 'auto' = the library's own split).
+"""Launch time against the number of clips handed to the flat kernel (set_flat_clips; 'auto' = the library's own split).
     python tools/flat_time.py"""
 import os
 import sys
@@ -15,10 +15,7 @@ for M in (80, 128):
         pcm = 0.1 * torch.randn(B, 480000, device="cuda", generator=g)
         out = torch.empty(B, M, 3000, device="cuda")
         for nflat in (0, 16, 32, 48, 64, 80, 96, "auto"):
-            if nflat == "auto":
-                os.environ.pop("WLM_FLAT_CLIPS", None)
-            else:
-                os.environ["WLM_FLAT_CLIPS"] = str(nflat)
+            fe.set_flat_clips(-1 if nflat == "auto" else nflat)
             for _ in range(3):
                 fe.extract_device(pcm, out=out)
             torch.cuda.synchronize()

@@ -25,15 +25,16 @@ for m in (80, 128):
             kind = rng.integers(0, 3, size=B)
             L = np.where(kind == 0, rng.integers(0, 480001, size=B), np.where(kind == 1, rng.integers(0, 20000, size=B), 480000))
             lens = torch.tensor(L, dtype=torch.int32, device="cuda")
-        os.environ["WLM_FLAT_CLIPS"] = "0"
+        fe.set_flat_clips(0)
         ref = fe.extract_device(pcm, lengths=lens).clone()
         for rep in range(4):
-            os.environ["WLM_FLAT_CLIPS"] = str(int(rng.integers(0, B))) if rep else "0"
+            nflat = int(rng.integers(0, B)) if rep else 0
+            fe.set_flat_clips(nflat)
             got = fe.extract_device(pcm, lengths=lens)
             if not torch.equal(got, ref):
                 bad += 1
                 d = (got - ref).abs()
-                print(f"MISMATCH m={m} round={r} B={B} ragged={ragged} flat={os.environ['WLM_FLAT_CLIPS']} max={d.max().item():.3e} "
+                print(f"MISMATCH m={m} round={r} B={B} ragged={ragged} flat={nflat} max={d.max().item():.3e} "
                       f"clips={torch.nonzero(d.amax(dim=(1, 2)) > 0).flatten().tolist()[:8]}")
         assert torch.isfinite(ref).all()
     fe.close()

@@ -18,6 +18,9 @@ WLM_ERR_NO_DEVICE = -4
 WLM_ERR_WORKSPACE = -5
 WLM_PCM_F32 = 0
 WLM_PCM_I16 = 1
+WLM_OUT_F32 = 0
+WLM_OUT_BF16 = 1
+WLM_OUT_F16 = 2
 
 # every symbol include/wlm.h declares: (restype, argtypes)
 _vp, _i, _i64, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
@@ -36,6 +39,9 @@ SYMBOLS = {
     "wlm_frame_mask": (_i, [_vp, _vp, _i, _vp, _vp]),
     "wlm_logmel_host": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "wlm_plan_launch_count": (_i64, [_vp]),
+    "wlm_plan_set_output_format": (_i, [_vp, _i]),
+    "wlm_plan_output_format": (_i, [_vp]),
+    "wlm_plan_set_flat_clips": (_i, [_vp, _i]),
 }
 
 

@@ -33,6 +33,37 @@ def _deps():
     return out
 
 
+def kernel_sources_sha() -> str:
+    """sha256 over the sources libwlm.so is compiled from (csrc/* + include/wlm.h), in name order.  bench.py prints ncu
+    traffic figures only when the committed profile summary was taken from a build of exactly these sources."""
+    import hashlib
+
+    h = hashlib.sha256()
+    for d in _deps():
+        h.update(os.path.basename(d).encode() + b"\0")
+        h.update(open(d, "rb").read())
+    return h.hexdigest()[:16]
+
+
+UBENCH_SRC = os.path.join(ROOT, "tools", "ubench_peak.cu")
+UBENCH_LIB = os.path.join(ROOT, "tools", "libwlm_ubench.so")
+
+
+def build_ubench(force: bool = False) -> str:
+    """tools/libwlm_ubench.so: the FFMA peak microbenchmark bench.py uses for the "of measured" FP32 roofline."""
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not force and os.path.exists(UBENCH_LIB) and os.path.getmtime(UBENCH_LIB) >= os.path.getmtime(UBENCH_SRC):
+        return UBENCH_LIB
+    if not os.path.exists(nvcc):
+        raise RuntimeError("nvcc not found")
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-shared", "-Xcompiler", "-fPIC",
+           "-o", UBENCH_LIB, UBENCH_SRC]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    return UBENCH_LIB
+
+
 def needs_build() -> bool:
     if not os.path.exists(LIB_PATH):
         return True
@@ -48,8 +79,6 @@ def build_library(force: bool = False, verbose: bool = False, extra_flags=()) ->
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
     flags = list(NVCC_FLAGS)
-    if os.path.exists(os.path.join(CSRC, "logmel_fused.cuh")):
-        flags.append("-DWLM_HAVE_FUSED")
     cmd = [nvcc, *flags, *extra_flags, "-I", os.path.join(ROOT, "include"), "-I", CSRC,
            "-o", LIB_PATH, *_sources()]
     if verbose:
@@ -66,3 +95,5 @@ def build_library(force: bool = False, verbose: bool = False, extra_flags=()) ->
 
 if __name__ == "__main__":
     print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_ubench(force="--force" in sys.argv))
+    print("kernel sources sha:", kernel_sources_sha())

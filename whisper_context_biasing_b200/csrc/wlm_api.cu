@@ -4,18 +4,17 @@
 // validation, launch sequencing, the pinned-ring H2D pipeline of wlm_logmel_host.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
-#ifdef WLM_HAVE_FUSED
 #include "logmel_fused.cuh"
-#endif
-#include "logmel_v0.cuh"
 #include "wlm_common.cuh"
 
 using namespace wlm;
@@ -50,25 +49,14 @@ struct wlm_plan {
     int device = -1;
     int n_mels = 0;
     int sm_count = 0;
-#ifdef WLM_HAVE_FUSED
-    int impl = 1;  // 1 = fused cluster kernel (product); 0 = v0 bring-up path (WLM_IMPL=v0, debug)
-#else
-    int impl = 0;
-#endif
     std::atomic<int64_t> launches{0};
+    int out_format = WLM_OUT_F32;
+    int flat_override = -1;        // clips for the flat kernel (dense batches); -1 = the library's split
 
-    // constant tables (device)
-    float2* d_tw = nullptr;        // [400] (cos, -sin)
-    float* d_win = nullptr;        // [400]
-    float* d_mel_dense = nullptr;  // [n_mels][201]
-    int16_t* d_klo = nullptr;      // [n_mels]
-    int16_t* d_khi = nullptr;      // [n_mels]
-    MelSparse* d_sparse = nullptr;
+    // constant tables: the sparse mel form travels in the constant bank (kernel argument), the window on the device
     MelSparse h_sparse;
-#ifdef WLM_HAVE_FUSED
     fused::Tables* d_fused_tables = nullptr;
     fused::Tables h_fused_tables;
-#endif
     int max_clusters = 0;          // co-resident clusters of the fused kernel (occupancy query)
     int flat_ctas = 0;             // SMs the clusters cannot cover: they run the flat kernel (programmatic dependent launch)
     int variant = 0;               // 80 / 128: unrolled mel stage (Whisper banks); 0: table-driven
@@ -163,23 +151,9 @@ extern "C" int wlm_plan_create(int device, int n_mels, const float* mel_dense_ho
     p->device = device;
     p->n_mels = n_mels;
     p->sm_count = prop.multiProcessorCount;
-    const char* impl_env = getenv("WLM_IMPL");
-    if (impl_env && strcmp(impl_env, "v0") == 0) p->impl = 0;
-
     std::vector<int16_t> klo, khi;
     int rc = build_sparse(mel_dense_host, n_mels, &p->h_sparse, &klo, &khi);
     if (rc != WLM_OK) { delete p; return rc; }
-
-    std::vector<float2> tw(kNfft);
-    std::vector<float> win(kNfft);
-    for (int j = 0; j < kNfft; ++j) {
-        const double ang = 2.0 * M_PI * j / kNfft;
-        tw[j] = make_float2((float)cos(ang), (float)-sin(ang));
-        win[j] = (float)(0.5 - 0.5 * cos(ang));  // periodic Hann, TF-FE:141
-    }
-    std::vector<float> melT((size_t)n_mels * kNFreq);
-    for (int k = 0; k < kNFreq; ++k)
-        for (int m = 0; m < n_mels; ++m) melT[(size_t)m * kNFreq + k] = mel_dense_host[k * n_mels + m];
 
 #define WLM_CUDA_P(expr)                                                                          \
     do {                                                                                          \
@@ -190,20 +164,6 @@ extern "C" int wlm_plan_create(int device, int n_mels, const float* mel_dense_ho
         }                                                                                         \
     } while (0)
 
-    WLM_CUDA_P(cudaMalloc(&p->d_tw, sizeof(float2) * kNfft));
-    WLM_CUDA_P(cudaMalloc(&p->d_win, sizeof(float) * kNfft));
-    WLM_CUDA_P(cudaMalloc(&p->d_mel_dense, sizeof(float) * melT.size()));
-    WLM_CUDA_P(cudaMalloc(&p->d_klo, sizeof(int16_t) * n_mels));
-    WLM_CUDA_P(cudaMalloc(&p->d_khi, sizeof(int16_t) * n_mels));
-    WLM_CUDA_P(cudaMalloc(&p->d_sparse, sizeof(MelSparse)));
-    WLM_CUDA_P(cudaMemcpy(p->d_tw, tw.data(), sizeof(float2) * kNfft, cudaMemcpyHostToDevice));
-    WLM_CUDA_P(cudaMemcpy(p->d_win, win.data(), sizeof(float) * kNfft, cudaMemcpyHostToDevice));
-    WLM_CUDA_P(cudaMemcpy(p->d_mel_dense, melT.data(), sizeof(float) * melT.size(), cudaMemcpyHostToDevice));
-    WLM_CUDA_P(cudaMemcpy(p->d_klo, klo.data(), sizeof(int16_t) * n_mels, cudaMemcpyHostToDevice));
-    WLM_CUDA_P(cudaMemcpy(p->d_khi, khi.data(), sizeof(int16_t) * n_mels, cudaMemcpyHostToDevice));
-    WLM_CUDA_P(cudaMemcpy(p->d_sparse, &p->h_sparse, sizeof(MelSparse), cudaMemcpyHostToDevice));
-
-#ifdef WLM_HAVE_FUSED
     {
         if (fused::build_tables(p->h_sparse, n_mels, &p->h_fused_tables, &p->variant) != 0) {
             wlm_plan_destroy(p);
@@ -219,8 +179,9 @@ extern "C" int wlm_plan_create(int device, int n_mels, const float* mel_dense_ho
         // the SMs that whole clusters cannot cover run the flat kernel (WLM_FLAT=0 turns that off)
         const char* fl = getenv("WLM_FLAT");
         p->flat_ctas = (fl && atoi(fl) == 0) ? 0 : std::max(0, p->sm_count - fused::kCluster * p->max_clusters);
+        // read ONCE (not per launch); clamped to [0, B - 1] when used
+        if (const char* fc = getenv("WLM_FLAT_CLIPS")) p->flat_override = std::max(-1, atoi(fc));
     }
-#endif
 
     WLM_CUDA_P(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
     for (auto& ev : p->ev_chunk) WLM_CUDA_P(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -235,11 +196,7 @@ extern "C" int wlm_plan_destroy(wlm_plan* p) {
     if (!p) return WLM_OK;
     cudaSetDevice(p->device);
     cudaDeviceSynchronize();
-    cudaFree(p->d_tw); cudaFree(p->d_win); cudaFree(p->d_mel_dense); cudaFree(p->d_klo); cudaFree(p->d_khi);
-    cudaFree(p->d_sparse);
-#ifdef WLM_HAVE_FUSED
     cudaFree(p->d_fused_tables);
-#endif
     cudaFree(p->d_stage); cudaFree(p->d_offsets); cudaFree(p->d_lengths); cudaFree(p->d_ws);
     for (auto& r : p->h_ring) if (r) cudaFreeHost(r);
     if (p->h_offsets) cudaFreeHost(p->h_offsets);
@@ -258,6 +215,20 @@ extern "C" int wlm_plan_sm_count(const wlm_plan* p) { return p ? p->sm_count : f
 extern "C" int wlm_plan_kernel_variant(const wlm_plan* p) { return p ? p->variant : fail(WLM_ERR_BAD_ARG, "plan is NULL"); }
 extern "C" int wlm_plan_max_clusters(const wlm_plan* p) { return p ? p->max_clusters : fail(WLM_ERR_BAD_ARG, "plan is NULL"); }
 extern "C" int64_t wlm_plan_launch_count(const wlm_plan* p) { return p ? p->launches.load() : -1; }
+extern "C" int wlm_plan_output_format(const wlm_plan* p) { return p ? p->out_format : fail(WLM_ERR_BAD_ARG, "plan is NULL"); }
+extern "C" int wlm_plan_set_output_format(wlm_plan* p, int out_format) {
+    if (!p) return fail(WLM_ERR_BAD_ARG, "plan is NULL");
+    if (out_format != WLM_OUT_F32 && out_format != WLM_OUT_BF16 && out_format != WLM_OUT_F16)
+        return fail(WLM_ERR_BAD_ARG, "unknown out_format %d", out_format);
+    p->out_format = out_format;
+    return WLM_OK;
+}
+extern "C" int wlm_plan_set_flat_clips(wlm_plan* p, int n_flat) {
+    if (!p) return fail(WLM_ERR_BAD_ARG, "plan is NULL");
+    p->flat_override = n_flat < 0 ? -1 : n_flat;
+    return WLM_OK;
+}
+static size_t out_elem_size(const wlm_plan* p) { return p->out_format == WLM_OUT_F32 ? 4 : 2; }
 
 extern "C" size_t wlm_workspace_bytes(const wlm_plan* p, int B) {
     if (!p || B <= 0) return 0;
@@ -268,32 +239,19 @@ extern "C" size_t wlm_workspace_bytes(const wlm_plan* p, int B) {
 // launch
 // ------------------------------------------------------------------------------------------
 static int launch_logmel(wlm_plan* p, const ClipArgs& a, cudaStream_t st) {
-    if (p->impl == 0) {
-        v0::init_gmax<<<(a.B + 255) / 256, 256, 0, st>>>(a.gmax, a.B);
-        dim3 grid((kNFrames + v0::kFramesPerCta - 1) / v0::kFramesPerCta, a.B);
-        v0::logmel_k1<<<grid, v0::kThreads, 0, st>>>(a, p->d_tw, p->d_win, p->d_mel_dense, p->d_klo, p->d_khi);
-        const int64_t total4 = (int64_t)a.B * a.n_mels * kNFrames / 4;
-        int blocks = (int)std::min<int64_t>((total4 + 255) / 256, (int64_t)p->sm_count * 16);
-        v0::logmel_k2<<<blocks, 256, 0, st>>>(a.out, a.gmax, a.n_mels, a.B);
-        p->launches += 3;
-    }
-#ifdef WLM_HAVE_FUSED
-    else {
-        int n_launches = 0;
-        bool flat_broken = false;
-        cudaError_t e = fused::launch(a, p->d_fused_tables, p->h_fused_tables, p->variant, p->max_clusters, st, &n_launches,
-                                      p->flat_ctas, &flat_broken);
-        if (flat_broken) p->flat_ctas = 0;
-        if (e != cudaSuccess) return fail(WLM_ERR_CUDA, "fused launch failed: %s", cudaGetErrorString(e));
-        p->launches += n_launches;
-    }
-#endif
+    int n_launches = 0;
+    bool flat_broken = false;
+    cudaError_t e = fused::launch(a, p->d_fused_tables, p->h_fused_tables, p->variant, p->max_clusters, st, &n_launches,
+                                  p->flat_ctas, p->flat_override, &flat_broken);
+    if (flat_broken) p->flat_ctas = 0;
+    if (e != cudaSuccess) return fail(WLM_ERR_CUDA, "fused launch failed: %s", cudaGetErrorString(e));
+    p->launches += n_launches;
     WLM_CUDA(cudaGetLastError());
     return WLM_OK;
 }
 
 extern "C" int wlm_logmel(wlm_plan* p, const void* pcm_dev, int pcm_format, const int64_t* offsets_dev,
-                          const int32_t* lengths_dev, int64_t row_stride, int B, float* out_dev,
+                          const int32_t* lengths_dev, int64_t row_stride, int B, void* out_dev,
                           float* gmax_dev, void* workspace, size_t workspace_bytes, void* stream) {
     if (!p) return fail(WLM_ERR_BAD_ARG, "plan is NULL");
     if (B < 0) return fail(WLM_ERR_BAD_ARG, "B=%d is negative", B);
@@ -330,6 +288,7 @@ extern "C" int wlm_logmel(wlm_plan* p, const void* pcm_dev, int pcm_format, cons
     a.clip_first = 0;
     a.out = out_dev;
     a.gmax = gmax;
+    a.out_format = p->out_format;
     return launch_logmel(p, a, static_cast<cudaStream_t>(stream));
 }
 
@@ -372,7 +331,7 @@ static bool is_pinned_host(const void* ptr) {
 }
 
 extern "C" int wlm_logmel_host(wlm_plan* p, const void* const* clips_host, const int32_t* lengths_host,
-                               int pcm_format, int B, float* out_dev, float* out_host, void* stream) {
+                               int pcm_format, int B, void* out_dev, void* out_host, void* stream) {
     if (!p) return fail(WLM_ERR_BAD_ARG, "plan is NULL");
     if (B < 0) return fail(WLM_ERR_BAD_ARG, "B=%d is negative", B);
     if (B == 0) return WLM_OK;
@@ -423,6 +382,43 @@ extern "C" int wlm_logmel_host(wlm_plan* p, const void* const* clips_host, const
         p->d_ws = nullptr; p->d_ws_bytes = 0;
         WLM_CUDA(cudaMalloc(&p->d_ws, ws_need));
         p->d_ws_bytes = ws_need;
+    }
+    // Small pageable batches -- the reference's own call shape, ONE clip per call (REF/data_utils/data_loader.py:171):
+    // no ring bounce, no copy stream, no events.  cudaMemcpyAsync from pageable memory returns once the source has been
+    // staged by the driver, so the host buffers are reusable on return without any synchronisation here.
+    bool small_pageable = (size_t)total_el * esz <= (4u << 20);
+    for (int b = 0; small_pageable && b < B; ++b)
+        if (p->h_lengths[b] > 0 && is_pinned_host(clips_host[b])) small_pageable = false;
+    if (small_pageable) {
+        for (int b = 0; b < B; ++b)
+            if (p->h_lengths[b] > 0)
+                WLM_CUDA(cudaMemcpyAsync(static_cast<char*>(p->d_stage) + p->h_offsets[b] * esz, clips_host[b],
+                                         (size_t)p->h_lengths[b] * esz, cudaMemcpyHostToDevice, st));
+        WLM_CUDA(cudaMemcpyAsync(p->d_offsets, p->h_offsets, sizeof(int64_t) * B, cudaMemcpyHostToDevice, st));
+        WLM_CUDA(cudaMemcpyAsync(p->d_lengths, p->h_lengths, sizeof(int32_t) * B, cudaMemcpyHostToDevice, st));
+        ClipArgs a;
+        a.pcm = p->d_stage;
+        a.offsets = p->d_offsets;
+        a.lengths = p->d_lengths;
+        a.row_stride = 0;
+        a.dense_len = 0;
+        a.pcm_format = pcm_format;
+        a.n_mels = p->n_mels;
+        a.B = B;
+        a.clip_first = 0;
+        a.out = out_dev;
+        a.gmax = static_cast<float*>(p->d_ws);
+        a.out_format = p->out_format;
+        int rc = launch_logmel(p, a, st);
+        if (rc != WLM_OK) return rc;
+        WLM_CUDA(cudaEventRecord(p->ev_kernels_done, st));
+        p->kernels_done_valid = true;
+        if (out_host) {
+            WLM_CUDA(cudaMemcpyAsync(out_host, out_dev, out_elem_size(p) * (size_t)B * p->n_mels * kNFrames,
+                                     cudaMemcpyDeviceToHost, st));
+            WLM_CUDA(cudaStreamSynchronize(st));
+        }
+        return WLM_OK;
     }
     WLM_CUDA(cudaMemcpyAsync(p->d_offsets, p->h_offsets, sizeof(int64_t) * B, cudaMemcpyHostToDevice, p->copy_stream));
     WLM_CUDA(cudaMemcpyAsync(p->d_lengths, p->h_lengths, sizeof(int32_t) * B, cudaMemcpyHostToDevice, p->copy_stream));
@@ -495,8 +491,9 @@ extern "C" int wlm_logmel_host(wlm_plan* p, const void* const* clips_host, const
         a.n_mels = p->n_mels;
         a.B = b1 - b0;
         a.clip_first = 0;
-        a.out = out_dev + (size_t)b0 * p->n_mels * kNFrames;
+        a.out = static_cast<char*>(out_dev) + (size_t)b0 * p->n_mels * kNFrames * out_elem_size(p);
         a.gmax = static_cast<float*>(p->d_ws) + b0;
+        a.out_format = p->out_format;
         int rc = launch_logmel(p, a, st);
         if (rc != WLM_OK) return rc;
         b0 = b1;
@@ -505,7 +502,7 @@ extern "C" int wlm_logmel_host(wlm_plan* p, const void* const* clips_host, const
     WLM_CUDA(cudaEventRecord(p->ev_kernels_done, st));
     p->kernels_done_valid = true;
     if (out_host) {
-        WLM_CUDA(cudaMemcpyAsync(out_host, out_dev, sizeof(float) * (size_t)B * p->n_mels * kNFrames,
+        WLM_CUDA(cudaMemcpyAsync(out_host, out_dev, out_elem_size(p) * (size_t)B * p->n_mels * kNFrames,
                                  cudaMemcpyDeviceToHost, st));
         WLM_CUDA(cudaStreamSynchronize(st));
     }
@@ -514,18 +511,3 @@ extern "C" int wlm_logmel_host(wlm_plan* p, const void* const* clips_host, const
     return WLM_OK;
 }
 
-#if defined(WLM_TRACE) && defined(WLM_HAVE_FUSED)
-// debug builds only: copy the phase timeline of CTA 0 out of the device (see logmel_fused.cuh)
-extern "C" int wlm_debug_trace(unsigned long long* dst, size_t count) {
-    const size_t n = sizeof(fused::g_trace) / sizeof(unsigned long long);
-    if (count < n) return (int)n;
-    WLM_CUDA(cudaMemcpyFromSymbol(dst, fused::g_trace, sizeof(fused::g_trace)));
-    return (int)n;
-}
-extern "C" int wlm_debug_trace_clip(unsigned long long* dst, size_t count) {
-    const size_t n = sizeof(fused::g_trace_clip) / sizeof(unsigned long long);
-    if (count < n) return (int)n;
-    WLM_CUDA(cudaMemcpyFromSymbol(dst, fused::g_trace_clip, sizeof(fused::g_trace_clip)));
-    return (int)n;
-}
-#endif

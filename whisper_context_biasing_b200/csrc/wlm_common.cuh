@@ -36,8 +36,9 @@ struct ClipArgs {
     int32_t n_mels;
     int32_t B;                // clips [clip_first, B) are processed by this launch
     int32_t clip_first;
-    float* out;               // [B][n_mels][3000]
+    void* out;                // [B][n_mels][3000], element type out_format
     float* gmax;              // [B] (may be workspace)
+    int32_t out_format;       // WLM_OUT_*
 };
 
 }  // namespace wlm

@@ -88,13 +88,20 @@ class B200WhisperFeatureExtractor:
       output:  what `return_tensors=None` yields -- "device" (default): a CUDA `torch.Tensor`
                that stays in HBM for the model (`Trainer._prepare_input(...).to(device)` is then
                a no-op); "numpy": a host `np.ndarray` exactly like the reference returns.
+      feature_dtype:  torch.float32 (default, the reference's dtype), torch.bfloat16 or
+               torch.float16: element type the kernel STORES (round-to-nearest of the float32
+               value; the reference model runs under fp16 autocast, REF/scripts/train.py:250).
+
+    Deviations from the reference class, on purpose: non-default geometry / padding arguments
+    raise NotImplementedError; the object is bound to one CUDA device and (like every stateful
+    CUDA plan) is meant to be driven from one host thread and one stream at a time.
     """
 
     model_input_names = ["input_features"]          # TF-FE:67
 
     def __init__(self, feature_size=80, sampling_rate=16000, hop_length=160, chunk_length=30, n_fft=400,
                  padding_value=0.0, dither=0.0, return_attention_mask=False, device=None,
-                 output="device", **kwargs):
+                 output="device", feature_dtype=None, **kwargs):
         import torch
 
         if (sampling_rate, hop_length, chunk_length, n_fft) != (SAMPLING_RATE, HOP_LENGTH, CHUNK_LENGTH, N_FFT):
@@ -140,6 +147,9 @@ class B200WhisperFeatureExtractor:
         N.check(N.LIB.wlm_plan_create(dev.index, self.feature_size, table.ctypes.data, C.byref(handle)))
         self._plan = handle
         self._ws = None
+        self.feature_dtype = torch.float32
+        if feature_dtype is not None:
+            self.set_feature_dtype(feature_dtype)
 
     # -- lifecycle ---------------------------------------------------------------------------
     def close(self):
@@ -171,7 +181,27 @@ class B200WhisperFeatureExtractor:
         """SMs of the device; `sm_count - 6 * max_clusters` of them run the cluster-less twin of the kernel."""
         return int(N.LIB.wlm_plan_sm_count(self._plan))
 
+    def set_feature_dtype(self, dtype):
+        """Element type of the features the kernel stores: float32, bfloat16 or float16."""
+        import torch
+
+        fmt = {torch.float32: N.WLM_OUT_F32, torch.bfloat16: N.WLM_OUT_BF16, torch.float16: N.WLM_OUT_F16}.get(dtype)
+        if fmt is None:
+            raise ValueError(f"feature_dtype {dtype} not supported (float32, bfloat16, float16)")
+        N.check(N.LIB.wlm_plan_set_output_format(self._plan, fmt))
+        self.feature_dtype = dtype
+
+    def set_flat_clips(self, n: int = -1):
+        """Measurement knob: clips of a dense batch handed to the cluster-less twin of the kernel (-1 = the library's split)."""
+        N.check(N.LIB.wlm_plan_set_flat_clips(self._plan, int(n)))
+
     # -- helpers -----------------------------------------------------------------------------
+    def _check_out(self, out, B):
+        if (tuple(out.shape) != (B, self.feature_size, self.nb_max_frames) or out.dtype != self.feature_dtype
+                or not out.is_cuda or out.device != self.device or not out.is_contiguous()):
+            raise ValueError(f"out must be a contiguous {self.feature_dtype} tensor [B={B}, {self.feature_size}, "
+                             f"{self.nb_max_frames}] on {self.device}")
+
     def _stream(self):
         import torch
 
@@ -206,8 +236,8 @@ class B200WhisperFeatureExtractor:
             fmt = N.WLM_PCM_I16
         else:
             raise ValueError(f"pcm dtype {pcm.dtype} not supported (float32 or int16)")
-        if not pcm.is_contiguous():
-            pcm = pcm.contiguous()
+        if not pcm.is_contiguous() or pcm.data_ptr() % 16:
+            pcm = pcm.contiguous() if pcm.data_ptr() % 16 == 0 else pcm.clone(memory_format=torch.contiguous_format)
         if offsets is None:
             if pcm.dim() == 1:
                 pcm = pcm[None]
@@ -223,9 +253,9 @@ class B200WhisperFeatureExtractor:
         if lengths is not None and (lengths.dtype != torch.int32 or not lengths.is_cuda or lengths.shape[0] != B):
             raise ValueError("lengths must be a CUDA int32 tensor of shape [B]")
         if out is None:
-            out = torch.empty((B, self.feature_size, self.nb_max_frames), dtype=torch.float32, device=self.device)
-        elif out.shape != (B, self.feature_size, self.nb_max_frames) or out.dtype != torch.float32 or not out.is_contiguous():
-            raise ValueError("out must be a contiguous float32 CUDA tensor [B, n_mels, 3000]")
+            out = torch.empty((B, self.feature_size, self.nb_max_frames), dtype=self.feature_dtype, device=self.device)
+        else:
+            self._check_out(out, B)
         gmax = torch.empty((max(B, 1),), dtype=torch.float32, device=self.device) if return_gmax else None
         ws, need = self._workspace(B)
         if B:
@@ -258,7 +288,7 @@ class B200WhisperFeatureExtractor:
 
         B = len(clips)
         if B == 0:
-            return torch.empty((0, self.feature_size, self.nb_max_frames), dtype=torch.float32, device=self.device)
+            return torch.empty((0, self.feature_size, self.nb_max_frames), dtype=self.feature_dtype, device=self.device)
         dt = clips[0].dtype
         if dt == np.float32:
             fmt = N.WLM_PCM_F32
@@ -278,7 +308,15 @@ class B200WhisperFeatureExtractor:
             ptrs[b] = x.ctypes.data if x.shape[0] else None
             lens[b] = x.shape[0]
         if out is None:
-            out = torch.empty((B, self.feature_size, self.nb_max_frames), dtype=torch.float32, device=self.device)
+            out = torch.empty((B, self.feature_size, self.nb_max_frames), dtype=self.feature_dtype, device=self.device)
+        else:
+            self._check_out(out, B)
+        if out_host is not None:
+            want = np.float32 if self.feature_dtype == torch.float32 else (np.float16 if self.feature_dtype == torch.float16 else np.uint16)
+            if (not isinstance(out_host, np.ndarray) or out_host.dtype != want or not out_host.flags["C_CONTIGUOUS"]
+                    or out_host.shape != (B, self.feature_size, self.nb_max_frames)):
+                raise ValueError(f"out_host must be a C-contiguous {np.dtype(want)} ndarray [B={B}, {self.feature_size}, "
+                                 f"{self.nb_max_frames}] (bfloat16 features: uint16 bit patterns)")
         with torch.cuda.device(self.device):
             N.check(N.LIB.wlm_logmel_host(
                 self._plan, ptrs, lens, fmt, B, C.c_void_p(out.data_ptr()),
@@ -319,7 +357,7 @@ class B200WhisperFeatureExtractor:
             if x.dtype != torch.float32:
                 x = x.to(torch.float32)
             if x.is_cuda:
-                if x.shape[1] % 4:
+                if x.shape[1] % 4:         # rows must start on 16-byte boundaries (extract_device clones unaligned views)
                     x = torch.nn.functional.pad(x, (0, 4 - x.shape[1] % 4))
                 feats = self.extract_device(x)
                 lengths_np = np.full((x.shape[0],), min(raw_speech.shape[-1], self.n_samples), dtype=np.int32)
@@ -347,7 +385,7 @@ class B200WhisperFeatureExtractor:
         want = getattr(want, "value", want)
         out = LogMelBatch()
         if want == "np":
-            out["input_features"] = feats.cpu().numpy()
+            out["input_features"] = (feats.float() if feats.dtype == torch.bfloat16 else feats).cpu().numpy()
         elif want == "pt":
             out["input_features"] = feats
         else:
@@ -355,6 +393,12 @@ class B200WhisperFeatureExtractor:
         if return_attention_mask:                                                              # TF-FE:328-337
             lens_dev = torch.from_numpy(lengths_np).to(self.device)
             mask = self.frame_mask_device(lens_dev)
+            out["attention_mask"] = mask.cpu().numpy() if want == "np" else mask
+        elif return_attention_mask is None and self.return_attention_mask:
+            # The reference's quirk, kept: pad() falls back to the ctor attribute (TF-SU:135-137) and returns the
+            # SAMPLE-level mask [B, 480000], which TF-FE:328 then does not rescale because the call argument is None.
+            lens_dev = torch.from_numpy(lengths_np).to(self.device)
+            mask = (torch.arange(self.n_samples, device=self.device, dtype=torch.int32)[None, :] < lens_dev[:, None]).to(torch.int32)
             out["attention_mask"] = mask.cpu().numpy() if want == "np" else mask
         return out
 
