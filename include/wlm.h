@@ -112,10 +112,11 @@ int wlm_plan_set_output_format(wlm_plan* plan, int out_format);
 int wlm_plan_output_format(const wlm_plan* plan);
 
 /*
- * Debug / measurement knob: how many clips of a DENSE batch (no lengths) go to the cluster-less
- * twin of the kernel that runs on the SMs whole clusters cannot cover.  -1 (default) = the
- * library's own split.  The environment variable WLM_FLAT_CLIPS, read ONCE when the plan is
- * created, sets the initial value.  Values are clamped to [0, B - 1] at launch.
+ * Debug / measurement knob for the cluster-less twin of the kernel that runs on the SMs whole
+ * clusters cannot cover (both kernels pull clips from one queue): -1 (default) = the library's
+ * own rule; 0 = never launch it; n > 0 = it may take up to n clips of every batch, whatever
+ * the batch.  The environment variable WLM_FLAT_CLIPS, read ONCE when the plan is created,
+ * sets the initial value.
  */
 int wlm_plan_set_flat_clips(wlm_plan* plan, int n_flat);
 

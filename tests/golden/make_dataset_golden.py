@@ -78,7 +78,9 @@ def main():
     with open(os.path.join(jsonl_dir, "test.jsonl"), "w") as f:
         for r in rows:
             f.write(json.dumps(r) + "\n")
-    store, meta = {}, {"strategies": {}, "n": len(rows)}
+    store, meta = {}, {"strategies": {}, "n": len(rows), "pad": int(tok.pad_token_id),
+                       "sot": int(tok.convert_tokens_to_ids("<|startoftranscript|>")),
+                       "prev": int(tok.convert_tokens_to_ids("<|startofprev|>"))}
     hf = WhisperFeatureExtractor()
     for name, kw in STRATEGIES.items():
         random.seed(0)

@@ -546,3 +546,45 @@ def test_multi_process_shards_match_single_process(fe):
     assert sorted(got) == list(range(n_clips))
     for b in range(n_clips):
         assert got[b] == _sha(ref[b]), b
+
+
+def test_pcm_dataset_items_through_the_device_collator(fe):
+    """items of the PCM dataset variant (audio + the reference's own labels / bias spans, taken from the
+    golden the reference's `PromptWhisperDataset` produced) -> device collator -> one batched launch.  The features must
+    match the ones the reference's items carried (computed by its CPU extractor), the label half the reference collator."""
+    import json
+    import os
+    import sys
+
+    import torch
+
+    from whisper_context_biasing_b200 import B200DataCollatorSpeechSeq2SeqWithPadding
+
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, gold)
+    from make_dataset_golden import synth_audio_for
+
+    z = np.load(os.path.join(gold, "dataset_golden.npz"))
+    meta = json.loads(bytes(z["meta_json"]).decode())
+    rows = [json.loads(l) for l in open(os.path.join(gold, "dataset_golden_rows.jsonl"))]
+    ex = fe[80]
+    coll = B200DataCollatorSpeechSeq2SeqWithPadding(feature_extractor=ex, pad_token_id=meta["pad"],
+                                                    decoder_start_token_id=meta["sot"], decoder_prev_token_id=meta["prev"])
+    for name in ("desc", "none"):
+        g = meta["strategies"][name]["items"]
+        items = []
+        for i, r in enumerate(rows):
+            audio, _ = synth_audio_for(os.path.join("/nonexistent", "test", r["file"]))
+            assert _sha(audio) == g[i]["pcm_sha256"]
+            items.append({"audio": audio, "labels": g[i]["labels"], "bias_spans": g[i]["bias_spans"]})
+        n0 = ex.launch_count
+        batch = coll(items)
+        assert ex.launch_count - n0 <= 2                        # ONE batched extraction for the whole batch
+        feats = batch["input_features"]
+        assert feats.is_cuda and tuple(feats.shape) == (len(rows), 80, 3000)
+        sub = feats[:, :, ::37].cpu().numpy()
+        for i in range(len(rows)):
+            assert np.abs(sub[i] - z[f"{name}_{i}_features_sub"]).max() <= TOL, (name, i)
+        assert batch["labels"].shape[0] == len(rows) and batch["bias_spans"].dim() == 3
+        if name == "desc":
+            assert (batch["labels"][:, 0] == -100).all()        # the prompt is masked up to <|startoftranscript|>

@@ -1,24 +1,26 @@
 // Fused log-mel kernel for sm_100a.
 //
-// A thread-block CLUSTER of 6 CTAs owns one clip.  Every CTA runs TWO independent warp groups of 8
-// warps ("virtual CTAs"); the clip's 3000 frames are 94 half-tiles of 32 frames and half-tile u goes
-// to virtual CTA u mod 12 (= 2 * cluster rank + group).  A group walks its half-tiles through
+// A thread-block CLUSTER of 6 CTAs owns one clip.  Every CTA holds TWO independent warp groups ("virtual CTAs"); the
+// clip's 3000 frames are 94 half-tiles of 32 frames and half-tile u goes to virtual CTA u mod 12 (= 2 * cluster rank +
+// group).  The warps of a CTA are SPECIALISED (registers re-balanced with setmaxnreg):
 //
-//   TMA (cp.async.bulk, mbarrier)  raw PCM  ->  shared memory, two sub-regions 16 banks apart
-//   stage 1  per warp: 4 frames x 16 sub-transforms; lane = (n1, sub-region); 25-point real DFT of
-//            the Hann-windowed samples n = (25 n1 + 16 n2) mod 400, packed f32x2 over two frames
-//   stage 2  the SAME warp, on its own two frame pairs: lane = (k2 slot, pair), 26 lanes; 16-point
-//            complex DFT over n1, |X|^2.  The hand-over is a __syncwarp (Y is private to the warp).
-//   mel      per warp: a run of <= 16 filters, lane = frame; sparse gather; mel POWER retained in
-//            TENSOR MEMORY (tcgen05.st), running max in registers
+//   FRONT END  2 groups x 8 warps, 104 registers.  Per half-tile, back to back:
+//     TMA (cp.async.bulk, mbarrier)  raw PCM  ->  shared memory, two sub-regions 16 banks apart
+//     stage 1  per warp: 4 frames x 16 sub-transforms; lane = (n1, sub-region); 25-point real DFT of
+//              the Hann-windowed samples n = (25 n1 + 16 n2) mod 400, packed f32x2 over two frames
+//     stage 2  the SAME warp, on its own two frame pairs: lane = (k2 slot, pair), 26 lanes; 16-point
+//              complex DFT over n1, |X|^2 -> P.  The hand-over is a __syncwarp (Y is private to the warp).
+//   BACK END   4 warps (2 per group), 64 registers, lane = frame:
+//     mel      sparse gather over P, four runs of <= 16 filters per warp; mel POWER retained in
+//              TENSOR MEMORY (tcgen05.st), running max in registers
+//     clip end the 12 virtual CTAs deliver their maxima to each other through distributed shared memory
+//              (st.async completing bytes on the receiver's mbarrier: nobody waits)
+//     output   the retained power is read back (tcgen05.ld) one half-tile per step of the NEXT clip and written as
+//              (max(log10(max(p,1e-10)), gmax - 8) + 4) / 4 -- the features touch HBM exactly once.
 //
-// with the prime-factor index maps of fft_pfa.cuh (no twiddles between the stages).  The FFT
-// arithmetic is FADD2 / FMUL2 / FFMA2 on (frame a, frame b) pairs with immediate constants.
-// The two groups share nothing but the clip-end exchange.  When the clip is done the 12 virtual
-// CTAs deliver their maxima to each other through distributed shared memory (st.async completing
-// bytes on the receiver's mbarrier: nobody waits), and the retained mel power is read back
-// (tcgen05.ld) one half-tile per step of the NEXT clip and written as
-// (max(log10(max(p,1e-10)), gmax - 8) + 4) / 4 -- the features touch HBM exactly once.
+// with the prime-factor index maps of fft_pfa.cuh (no twiddles between the stages).  The FFT arithmetic is
+// FADD2 / FMUL2 / FFMA2 on (frame a, frame b) pairs with immediate constants.  The front end never sees a clip boundary:
+// it streams half-tiles; the only coupling to the back end is the P buffer (P full / P free mbarriers).
 //
 // Shared memory (bytes):  raw 2 x 22,400 | Y 2 x 54,272 | P 2 x 26,752 | mbarriers + scratch 1024
 #pragma once
@@ -61,8 +63,23 @@ namespace fused {
 constexpr int kGroups = 2;                // independent warp groups per CTA
 constexpr int kGroupWarps = 8;
 constexpr int kGroupThreads = kGroupWarps * 32;
-constexpr int kWarps = kGroups * kGroupWarps;
+constexpr int kFeWarps = kGroups * kGroupWarps;      // front end: the FFT stages
+#ifndef WLM_BE_WARPS
+#define WLM_BE_WARPS 4
+#endif
+constexpr int kBeWarps = WLM_BE_WARPS;               // back end: mel, retention, output (4 or 8: whole warpgroups)
+constexpr int kBePerGroup = kBeWarps / kGroups;
+constexpr int kRunsPerBe = kGroupWarps / kBePerGroup;   // filter runs (of <= 16 filters) per back-end warp
+constexpr int kWarps = kFeWarps + kBeWarps;
 constexpr int kThreads = kWarps * 32;
+// Registers per thread.  The CTA is launched with kLaunchRegs each (the most 640 threads can have in allocation units of
+// 8); setmaxnreg then moves registers from the back-end warps to the front-end warps INSIDE the CTA's own allocation:
+// 16 x kFeRegs + kBeWarps x kBeRegs <= kWarps x kLaunchRegs (an increase beyond the pool would spin forever).
+constexpr int kLaunchRegs = 65536 / kThreads / 8 * 8;                                   // 96
+constexpr int kBeRegs = kBeWarps == 4 ? 64 : 48;
+constexpr int kFeRegs = (kWarps * kLaunchRegs - kBeWarps * kBeRegs) / kFeWarps / 8 * 8;   // 104
+static_assert(kFeWarps * kFeRegs + kBeWarps * kBeRegs <= kWarps * kLaunchRegs, "setmaxnreg must stay inside the CTA's pool");
+static_assert(kBeWarps == 4 || kBeWarps == 8, "back-end warps come in warpgroups of four (setmaxnreg, TMEM lane quarters)");
 constexpr int kTile = 4 * kGroupWarps;    // frames per half-tile (the unit of work of one group): 2 pairs per warp
 constexpr int kPairs = kTile / 2;         // 16 frame pairs
 constexpr int kTilesPerClip = (kNFrames + kTile - 1) / kTile;  // 94
@@ -100,9 +117,12 @@ constexpr int kVCluster = kCluster * kGroups;   // 12 virtual CTAs per clip
 constexpr int kMaxTilesPerGroup = (kTilesPerClip + kVCluster - 1) / kVCluster;   // 8
 constexpr int kMaxFiltersPerWarp = 16;          // 8 warps x 16 >= 128 mels
 constexpr int kMaxGroupBins = 16;               // bins between two adjacent filter centres
-constexpr int kTmemColsPerTile = kMaxFiltersPerWarp;                          // 16 (lane = frame)
-constexpr int kTmemColsPerWarp = kMaxTilesPerGroup * kTmemColsPerTile;        // 128; 4 warps per lane quarter = 512 columns
-static_assert(4 * kTmemColsPerWarp <= 512, "the retained mel power must fit the 512 TMEM columns");
+// Tensor memory: lane quarter q (TMEM lanes [32 q, +32), lane = frame) belongs to group q >> 1 and holds filter runs
+// 4 (q & 1) .. + 3 of that group's half-tiles: slot j (the j-th half-tile of the clip in this group) at columns
+// [64 j, +64), run r of the quarter at + 16 r.
+constexpr int kTmemColsPerRun = kMaxFiltersPerWarp;                           // 16
+constexpr int kTmemColsPerSlot = (kGroupWarps / 2) * kTmemColsPerRun;         // 64
+static_assert(kMaxTilesPerGroup * kTmemColsPerSlot <= 512, "the retained mel power must fit the 512 TMEM columns");
 static_assert(kVCluster <= 32, "max reduction over the cluster uses one warp");
 
 // float2 index, inside a pair's row of P, of FFT bin k (stage 2 stores position i of slot s at 13 i + s)
@@ -209,28 +229,39 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+// Waiting must be cheap: a warp that spins on try_wait issues an instruction every other cycle and takes the issue
+// slots of the warps that share its scheduler (profiles/r02: a third of all executed instructions were polls).  One
+// immediate test, then sleep between polls.  WLM_WAIT_NS: sleep per poll (ns); the back end, which has slack, sleeps longer.
+#ifndef WLM_WAIT_NS
+#define WLM_WAIT_NS 32
+#endif
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t done;
     asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(bar), "r"(parity) : "memory");
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    return done != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_test(bar, parity)) return;
+    do { __nanosleep(WLM_WAIT_NS); } while (!mbar_test(bar, parity));
+}
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+    if (mbar_test(bar, parity)) return;
+    do { __nanosleep(4 * WLM_WAIT_NS); } while (!mbar_test(bar, parity));
 }
 // same, acquiring at cluster scope: the data the barrier guards was written by other CTAs of the cluster
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAITC_%=:\n"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONEC_%=;\n"
-        "bra WAITC_%=;\n"
-        "DONEC_%=:\n"
-        "}\n" ::"r"(bar), "r"(parity) : "memory");
+    while (true) {
+        uint32_t done;
+        asm volatile(
+            "{\n.reg .pred p;\n"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) break;
+        __nanosleep(4 * WLM_WAIT_NS);
+    }
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -543,20 +574,6 @@ __device__ __forceinline__ float mel_fixed_warp(const KernelTables& kt, const fl
     return mx;
 }
 
-template <int NMELS, class Sink>
-__device__ __forceinline__ float mel_fixed(const KernelTables& kt, const float* P, int wg, int lane, Sink sink) {
-    switch (wg) {
-        case 0: return mel_fixed_warp<NMELS, 0>(kt, P, lane, sink);
-        case 1: return mel_fixed_warp<NMELS, 1>(kt, P, lane, sink);
-        case 2: return mel_fixed_warp<NMELS, 2>(kt, P, lane, sink);
-        case 3: return mel_fixed_warp<NMELS, 3>(kt, P, lane, sink);
-        case 4: return mel_fixed_warp<NMELS, 4>(kt, P, lane, sink);
-        case 5: return mel_fixed_warp<NMELS, 5>(kt, P, lane, sink);
-        case 6: return mel_fixed_warp<NMELS, 6>(kt, P, lane, sink);
-        default: return mel_fixed_warp<NMELS, 7>(kt, P, lane, sink);
-    }
-}
-
 // log10(max(p, 1e-10)) == max(log10 p, -10): exactly -10 for silence (TF-FE:155); p = 0 -> -inf -> -10
 __device__ __forceinline__ float log10_floor(float p) {
     constexpr float kLog10_2 = 0.30102999566398120f;
@@ -575,35 +592,29 @@ template <> __device__ __forceinline__ float from_out<float>(float v) { return v
 template <> __device__ __forceinline__ float from_out<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
 template <> __device__ __forceinline__ float from_out<__half>(__half v) { return __half2float(v); }
 
-// The element type is a template parameter of the kernel (a run-time switch tripled the code of the output pass and
-// cost 6 % through the instruction cache): f(T*) is called with a.out as OutT*.
-template <class OutT, class F>
-__device__ __forceinline__ void with_out_type(const ClipArgs& a, F f) { f(static_cast<OutT*>(a.out)); }
+// calls f(T*) with the element type of a.out
+template <class F>
+__device__ __forceinline__ void with_out_type(const ClipArgs& a, F f) {
+    if (a.out_format == WLM_OUT_F32) f(static_cast<float*>(a.out));
+    else if (a.out_format == WLM_OUT_BF16) f(static_cast<__nv_bfloat16*>(a.out));
+    else f(static_cast<__half*>(a.out));
+}
 
 // ---- the clip queue -----------------------------------------------------------------------------------------------
 // Clips are handed out dynamically: a worker (a cluster, or a CTA of the flat kernel) takes clip `worker` first (its
-// ordinal 0) and every further one from the global counter, so ragged batches balance themselves and the flat CTAs can
-// work next to the clusters whatever the clip lengths.  The worker's LEADER (lane 0 of warp 0 of its first CTA) fetches
-// ahead of need, at the TOP of a loop iteration (before anything in the iteration can block), and publishes the clip of
-// ordinal n in slot n & 7 of a ring that sits in the shared memory of EVERY CTA of the worker (remote stores through
-// distributed shared memory), tagged with the ordinal; everybody else polls its local copy.
-//   cluster  ordinals 1 and 2 in the prologue; the atomic for ordinal n + 3 is ISSUED at the top of the leader's first
-//            iteration of clip n and its result PUBLISHED at the top of the following iteration (a global atomic takes
-//            1-2 us to return: consumed at once it stalled the leader's warp, and through the hand-overs its whole
-//            cluster, once per clip -- 6 % of the batch)
-//   flat     ordinal n + 1 at the top of the iteration four steps before the end of clip n -- a flat CTA needs ~7x
-//            longer per clip than a cluster, so it commits late, and only while `flat_reserve` clips are still
-//            unassigned (the clusters would otherwise sit idle waiting for it at the end of the batch)
-// Readers look at most two (flat: one) ordinals ahead of the clip they are working on, i.e. only at values the leader
-// published in an EARLIER iteration of its own program order; the leader's progress never depends on a reader that is
-// ahead of it (hand-overs inside a group only involve half-tiles the waiting warp has already finished), so no poll can
-// wait for itself.  A slot is reused eight ordinals later; a warp in clip n has waited for the maxima of clip n - 2 of
-// all virtual CTAs, so nobody can still be reading ordinal n - 6.
+// ordinal 0) and every further one from the global counter.  The worker's LEADER (one lane of a back-end warp of its first
+// CTA) fetches ahead of need and publishes the clip of ordinal n in slot n & 3 of a small ring that sits in the shared
+// memory of EVERY CTA of the worker (remote stores through distributed shared memory), tagged with the ordinal; everybody
+// else polls its local copy.  Fetch schedule (DESIGN.md section 4 argues that no reader ever waits for a fetch that
+// depends on the reader's own progress):
+//   cluster  ordinal 1 in the prologue; ordinal n + 2 when the leader starts clip n (after the maxima of clip n - 1 are in)
+//   flat     ordinal n + 1 four steps before the leader finishes clip n -- a flat CTA needs ~7x longer per clip than a
+//            cluster, so it commits late, and only while `flat_reserve` clips are still unassigned (the clusters would
+//            otherwise sit idle waiting for it at the end of the batch)
 constexpr int kClipEnd = 0x7fffffff;
-constexpr int kQueueRing = 8;
 __device__ __forceinline__ int queue_get(const unsigned long long* ring, int ord, int first) {
     if (ord == 0) return first;
-    const volatile unsigned long long* p = ring + (ord & (kQueueRing - 1));
+    const volatile unsigned long long* p = ring + (ord & 3);
     unsigned long long v;
     do { v = *p; } while (static_cast<uint32_t>(v >> 32) != static_cast<uint32_t>(ord + 1));
     return static_cast<int>(static_cast<uint32_t>(v));
@@ -612,9 +623,9 @@ template <bool FLAT, int NCTA>
 __device__ __forceinline__ void queue_put(unsigned long long* ring, int ord, int clip) {
     const unsigned long long v = (static_cast<unsigned long long>(static_cast<uint32_t>(ord + 1)) << 32) | static_cast<uint32_t>(clip);
     if constexpr (FLAT) {
-        *reinterpret_cast<volatile unsigned long long*>(ring + (ord & (kQueueRing - 1))) = v;
+        *reinterpret_cast<volatile unsigned long long*>(ring + (ord & 3)) = v;
     } else {
-        const uint32_t local = static_cast<uint32_t>(__cvta_generic_to_shared(ring + (ord & (kQueueRing - 1))));
+        const uint32_t local = static_cast<uint32_t>(__cvta_generic_to_shared(ring + (ord & 3)));
 #pragma unroll 1
         for (int r = 0; r < NCTA; ++r) {
             uint32_t remote;
@@ -642,77 +653,124 @@ __device__ __forceinline__ int queue_fetch(const ClipArgs& a, int taken) {
     }
 }
 
+// ---- the stream of steps of one warp group ("virtual CTA") ------------------------------------------
+// Inside a clip the virtual CTA `vrank` of `kVC` owns the half-tiles vrank, vrank + kVC, ... that hold real samples.  A
+// clip in which it owns none still yields one (empty) step, so that the back end takes part in that clip's max exchange.
+struct Stream {
+    int ord;            // ordinal of the clip among those of this worker
+    int b;              // clip
+    int j;              // step inside the clip
+    int n_my;           // half-tiles of mine in the clip
+    bool valid;
+    ClipCtx cc;
+};
+template <int VC>
+__device__ __forceinline__ int my_tiles(int n_act, int vrank) { return n_act > vrank ? (n_act - vrank + VC - 1) / VC : 0; }
+template <int VC>
+__device__ __forceinline__ void stream_open(Stream& s, const ClipArgs& a, int ord, int b, int vrank) {
+    s.ord = ord; s.b = b; s.j = 0; s.n_my = 0;
+    s.valid = b < a.B;
+    s.cc.b = b; s.cc.len = 0; s.cc.n_act = 0; s.cc.base = 0;
+    if (s.valid) {
+        s.cc = clip_ctx(a, b);
+        s.n_my = my_tiles<VC>(s.cc.n_act, vrank);
+    }
+}
+template <int VC>
+__device__ __forceinline__ void stream_advance(Stream& s, const ClipArgs& a, const unsigned long long* ring, int first, int vrank) {
+    const int steps = s.n_my > 0 ? s.n_my : 1;
+    if (s.j + 1 < steps) ++s.j;
+    else stream_open<VC>(s, a, s.ord + 1, queue_get(ring, s.ord + 1, first), vrank);
+}
+
+// mel stage of the filter runs W0 .. W0 + NR - 1 (one back-end warp), lane = frame; run(r, W, out[16]) receives each run
+template <int NMELS, int W0, int NR, class Run>
+__device__ __forceinline__ float mel_runs_fixed(const KernelTables& kt, const float* P, int lane, Run run) {
+    float mx = 0.f;
+    if constexpr (NR > 0) {
+        mx = mel_fixed_warp<NMELS, W0>(kt, P, lane, [&](const float (&o)[kMaxFiltersPerWarp]) { run(0, W0, o); });
+        if constexpr (NR > 1)
+            mx = fmaxf(mx, mel_runs_fixed<NMELS, W0 + 1, NR - 1>(kt, P, lane,
+                           [&](int r, int W, const float (&o)[kMaxFiltersPerWarp]) { run(r + 1, W, o); }));
+    }
+    return mx;
+}
+
+// the back-end warp whose first run is W0: table-driven (NMELS = 0) or unrolled with the Whisper bank's structure
+template <int NMELS, class Run>
+__device__ __forceinline__ float mel_be(const KernelTables& kt, const float* P, int W0, int lane, Run run) {
+    if constexpr (NMELS == 0) {
+        float mx = 0.f;
+#pragma unroll 1
+        for (int r = 0; r < kRunsPerBe; ++r)
+            mx = fmaxf(mx, mel_stage(kt, P, W0 + r, lane, [&](const float (&o)[kMaxFiltersPerWarp]) { run(r, W0 + r, o); }));
+        return mx;
+    } else {
+        if constexpr (kRunsPerBe == 4) {
+            if (W0 == 0) return mel_runs_fixed<NMELS, 0, 4>(kt, P, lane, run);
+            return mel_runs_fixed<NMELS, 4, 4>(kt, P, lane, run);
+        } else {
+            switch (W0) {
+                case 0: return mel_runs_fixed<NMELS, 0, 2>(kt, P, lane, run);
+                case 2: return mel_runs_fixed<NMELS, 2, 2>(kt, P, lane, run);
+                case 4: return mel_runs_fixed<NMELS, 4, 2>(kt, P, lane, run);
+                default: return mel_runs_fixed<NMELS, 6, 2>(kt, P, lane, run);
+            }
+        }
+    }
+}
+
 // ================================================================================================
-// The kernel: persistent clusters of 6 CTAs x 2 warp groups, one clip per cluster at a time.
+// The kernel: persistent clusters of 6 CTAs, one clip per cluster at a time; per CTA two groups of
+// 8 front-end warps (the FFT stages) and kBeWarps back-end warps (mel, retention, output).
 // ================================================================================================
 // NMELS = 80 / 128: unrolled mel stage for the Whisper banks; NMELS = 0: table-driven mel stage.
 //
 // FLAT = true is the same pipeline for the SMs that 6-CTA clusters cannot cover (clusters do not span GPCs: 22 of them fit,
 // 16 SMs stay idle; tools/ubench_corun.cu shows that a second kernel runs there undisturbed).  One CTA per clip, no cluster
-// and no tensor memory: the mel stage writes (log10 + 4) / 4 straight to HBM, and when the clip is done the CTA's 16 warps
-// meet once, take the clip's max and re-read the clip's 0.96 MB from L2 to apply the max - 8 clamp.
-// DYN = false: clips are assigned statically (worker w of W takes clip_first + w, + W, ...; dense batches, where every
-// clip costs the same and the host can split the batch between the two kernels up front); DYN = true: from the clip queue.
-template <int NMELS, bool FLAT, class OutT, bool DYN>
+// and no tensor memory: the back end writes (max(log10 p, -10) + 4) / 4 straight to HBM, and once the clip's max is known
+// re-reads its own rows (one half-tile per step, out of L2) to apply the max - 8 clamp in place.
+template <int NMELS, bool FLAT>
 __global__ void __launch_bounds__(kThreads, 1)
 logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt, const float* __restrict__ win_lane) {
     namespace cg = cooperative_groups;
     constexpr int kVC = FLAT ? kGroups : kVCluster;      // virtual CTAs (warp groups) that share a clip
-    constexpr int kCl = FLAT ? 1 : kCluster;
+    constexpr int kCl = FLAT ? 1 : kCluster;             // CTAs that share a clip
     extern __shared__ __align__(128) unsigned char smem[];
     // this CTA is resident: once all of them are, the flat kernel (a programmatic dependent launch) may take the free SMs
     if constexpr (!FLAT) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler
-    const int grp = warp / kGroupWarps, wg = warp % kGroupWarps;   // warp group and warp inside the group
 
-    unsigned char* gbase = smem + grp * kSmemGroup;
-    float* raw = reinterpret_cast<float*>(gbase);
-    float2* Y = reinterpret_cast<float2*>(gbase + kSmemRaw) + wg * kYWarpFloat2;      // this WARP's stage-1 output
-    float* P = reinterpret_cast<float*>(gbase + kSmemRaw + kSmemY);
     unsigned char* misc = smem + kGroups * kSmemGroup;
-    // mbarriers (8 B each), one set per group.  Inside a warp stage 1 hands over to stage 2 through the warp's own Y
-    // (__syncwarp); between warps there are only these: the shared raw buffer and the shared P buffer of the group.
-    unsigned char* gm = misc + grp * 64;
-    const uint32_t bar_raw = smem_u32(gm);           // TMA landed the half-tile's PCM              (tx, 1 arrival)
-    const uint32_t bar_pfull = smem_u32(gm + 24);    // all warps of the group stored the power of the half-tile
-    const uint32_t bar_pfree = smem_u32(gm + 32);    // all 8 warps finished the mel stage          (8)
-    uint32_t* raw_readers = reinterpret_cast<uint32_t*>(gm + 40);     // warps done with the raw buffer
     // clip-end max exchange (all indexed by clip parity): every virtual CTA of the cluster delivers its max into
     // clip_max of EVERY CTA (distributed shared memory, st.async) which completes bytes on that CTA's bar_max
     const uint32_t bar_max = smem_u32(misc + 256);                    // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 272);    // TMEM base address
-    uint32_t* grp_cnt = reinterpret_cast<uint32_t*>(misc + 288);      // [2][kGroups] warps of the group that have contributed
+    uint32_t* grp_cnt = reinterpret_cast<uint32_t*>(misc + 288);      // [2][kGroups] back-end warps of the group that have contributed
     int* grp_max = reinterpret_cast<int*>(misc + 320);                // [2][kGroups] running max of the group (float bits, >= 0)
     float* clip_max = reinterpret_cast<float*>(misc + 352);           // [2][kVCluster] written by the peers
-    unsigned long long* clipq = reinterpret_cast<unsigned long long*>(misc + 512);   // [8] the worker's clips by ordinal & 7
+    unsigned long long* clipq = reinterpret_cast<unsigned long long*>(misc + 512);   // [4] the worker's clips by ordinal & 3
 
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = FLAT ? 0 : static_cast<int>(cluster.block_rank());
-    const int vrank = rank * kGroups + grp;          // virtual CTA inside the clip
-    // the worker's first clip is its index; the rest come from the queue (DYN) or follow at a stride of W workers
-    const int worker = FLAT ? static_cast<int>(blockIdx.x) : static_cast<int>(blockIdx.x) / kCluster;
-    const int n_static = FLAT ? static_cast<int>(gridDim.x) : static_cast<int>(gridDim.x) / kCluster;
-    const int first_clip = DYN ? a.worker_base + worker : a.clip_first + worker;
-    const bool leader = DYN && rank == 0 && tid == 0;
-    // flat kernel: clip-end meeting of the CTA's 16 warps and the clip's max (ring of three: see D)
-    const uint32_t bar_clip = smem_u32(misc + 640);
-    int* flat_max = reinterpret_cast<int*>(misc + 656);
+    // the worker's first clip is its index; the rest come from the queue
+    const int first_clip = a.worker_base + (FLAT ? static_cast<int>(blockIdx.x) : static_cast<int>(blockIdx.x) / kCluster);
 
     if (tid == 0) {
         for (int g = 0; g < kGroups; ++g) {
             const uint32_t b = smem_u32(misc + g * 64);
-            mbar_init(b, 1);
-            mbar_init(b + 24, kGroupWarps);
-            mbar_init(b + 32, kGroupWarps);
+            mbar_init(b, 1);                      // raw landed          (tx bytes, 1 arrival)
+            mbar_init(b + 24, kGroupWarps);       // P full              (8 front-end warps)
+            mbar_init(b + 32, kBePerGroup);       // P free              (the group's back-end warps)
             *reinterpret_cast<uint32_t*>(misc + g * 64 + 40) = 0;
         }
-        mbar_init(bar_max, 1);          // one arrival (this CTA's group 0, with the byte count) + 12 x 4 bytes from the peers
-        mbar_init(bar_max + 8, 1);
+        // cluster: one arrival (this CTA's group 0, with the byte count) + kVC x 4 bytes from the peers (st.async);
+        // flat (no cluster, no distributed shared memory): one plain arrival per group
+        mbar_init(bar_max, FLAT ? kGroups : 1);
+        mbar_init(bar_max + 8, FLAT ? kGroups : 1);
         for (int i = 0; i < 2 * kGroups; ++i) { grp_cnt[i] = 0; grp_max[i] = 0; }
-        for (int i = 0; i < kQueueRing; ++i) clipq[i] = 0ull;
-        mbar_init(bar_clip, kWarps);
-        flat_max[0] = flat_max[1] = flat_max[2] = 0;
+        for (int i = 0; i < 4; ++i) clipq[i] = 0ull;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     uint32_t tmem_base = 0;
@@ -721,407 +779,321 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
     } else {
         if (warp == 0) tmem_alloc_512(smem_u32(tmem_slot));
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        cluster.sync();     // (also a CTA barrier) every peer's mbarriers and queue ring exist before anyone writes them remotely
+        cluster.sync();     // (also a CTA barrier) every peer's mbarriers exist before anyone can arrive on them remotely
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         tmem_base = *tmem_slot;
-        if (leader) {                                            // (DYN) ordinals 1 and 2 of this cluster: one atomic
-            const unsigned int c = static_cast<unsigned int>(a.n_workers) + atomicAdd(&a.queue->next, 2u);
-            queue_put<false, kCluster>(clipq, 1, c < static_cast<unsigned int>(a.B) ? static_cast<int>(c) : kClipEnd);
-            queue_put<false, kCluster>(clipq, 2, c + 1 < static_cast<unsigned int>(a.B) ? static_cast<int>(c + 1) : kClipEnd);
-        }
+        // ordinal 1 of this cluster, for all its CTAs (their rings exist: the cluster barrier above)
+        if (rank == 0 && tid == 0) queue_put<false, kCluster>(clipq, 1, queue_fetch<false>(a, 1));
     }
-    // the imaginary part of slot 0 in the warp's Y: zeros, written once (stage 1 never stores there)
-    Y[(lane >> 1) * kYN1 + kYLanes + (lane & 1)] = make_float2(0.f, 0.f);
-    __syncwarp();
-    // this warp's TMEM window: lane quarter (warp & 3), 128 columns at (warp >> 2) * 128
-    const uint32_t twin = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) +
-                          static_cast<uint32_t>((warp >> 2) * kTmemColsPerWarp);
 
-    // per-lane stage-1 constants
-    const int n1 = lane & 15;
-    float wv[25];
+    if (warp < kFeWarps) {
+        // ============================================================================================
+        // FRONT END: stage 1 and stage 2 of the group's half-tiles, back to back; never looks at a clip boundary.
+        //   wait raw | load | last warp re-arms TMA | FFT-25 | store (warp-private Y) | __syncwarp |
+        //   load own Y | FFT-16, |X|^2 | wait P free | store P | arrive P full
+        // ============================================================================================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kFeRegs));
+        const int grp = warp / kGroupWarps, wg = warp % kGroupWarps;
+        unsigned char* gbase = smem + grp * kSmemGroup;
+        float* raw = reinterpret_cast<float*>(gbase);
+        float2* Y = reinterpret_cast<float2*>(gbase + kSmemRaw) + wg * kYWarpFloat2;      // this WARP's stage-1 output
+        float* P = reinterpret_cast<float*>(gbase + kSmemRaw + kSmemY);
+        unsigned char* gm = misc + grp * 64;
+        const uint32_t bar_raw = smem_u32(gm), bar_pfull = smem_u32(gm + 24), bar_pfree = smem_u32(gm + 32);
+        uint32_t* raw_readers = reinterpret_cast<uint32_t*>(gm + 40);     // warps done with the raw buffer
+        const int vrank = rank * kGroups + grp;          // virtual CTA inside the clip
+        const int tg = tid & (kGroupThreads - 1);
+
+        // the imaginary part of slot 0 in the warp's Y: zeros, written once (stage 1 never stores there)
+        Y[(lane >> 1) * kYN1 + kYLanes + (lane & 1)] = make_float2(0.f, 0.f);
+        __syncwarp();
+        float wv[25];                                    // Hann window at this lane's 25 sample positions
 #pragma unroll
-    for (int t = 0; t < 25; ++t) wv[t] = win_lane[n1 * 25 + t];
+        for (int t = 0; t < 25; ++t) wv[t] = win_lane[(lane & 15) * 25 + t];
 
-    // The group's work is a stream of steps, one per half-tile it owns (a clip in which it owns no active
-    // half-tile still contributes one empty step so that it takes part in that clip's max exchange).
-    // Program order of every warp in step i (half-tile t_i):
-    //   Q  (leader lane) fetch a clip ahead and publish it to the worker's CTAs
-    //   A  stage 1 of t_i            wait raw | load | last warp re-arms TMA | FFT | store (warp-private Y) | __syncwarp
-    //   F  output pass of the clip that ended one step ago   (wait for the 12 maxima, TMEM read-back, stores)
-    //   B  mel stage of t_{i-1}      wait P full | ... | arrive P free
-    //   D  if t_{i-1} ended a clip:  warp max -> group max (atomic); the last warp delivers it to all 6 CTAs
-    //   C  stage 2 of t_i            load own Y | FFT | wait P free | store | arrive P full
-    // `c*` = the step whose half-tile is in stage 1 / stage 2, `p*` = the previous step (mel stage).
-    auto my_tiles = [&](int n_act) { return n_act > vrank ? (n_act - vrank + kVC - 1) / kVC : 0; };
-    int cord = 0;                                                   // ordinal of the current clip among this worker's
-    int cb = first_clip, cj = 0, cn_my = 0;                         // clip, step inside the clip, half-tiles of mine in the clip
-    bool cvalid = cb < a.B;
-    ClipCtx cc;
-    cc.b = cb; cc.len = 0; cc.n_act = 0; cc.base = 0;
-    if (cvalid) {
-        cc = clip_ctx(a, cb);
-        cn_my = my_tiles(cc.n_act);
-    }
-    bool pvalid = false, phas = false, plast = false;
-    int pb = 0, pj = 0, ptile = 0, pn_my = 0, pn_act = 0;
-    int clip_seq = 0;                        // (flat kernel) clips this warp has finished
-    int taken = FLAT ? 1 : 2;                // (leader) clips this worker has been given so far
-    bool q_end = false;                      // (leader) the queue has answered "no more"
-    // TMA target after (clip ordinal ord0, step j0): the next half-tile of the same clip, else the first half-tile of one
-    // of the next two (flat: one) clips of this worker in which this group owns one.  Executed by ONE lane (the last warp
-    // to finish reading raw).  Returns false if the target is not known yet: the lane then OWES the copy and issues it when
-    // its own warp arrives at that half-tile (rare: clips so short that the group idles anyway).
-    auto issue_next_tile = [&](int ord0, const ClipCtx& c0, int n_my0, int j0) -> bool {
-        if (j0 + 1 < n_my0) {
-            tile_issue_tma(a, c0, vrank + (j0 + 1) * kVC, raw, bar_raw);
-            return true;
-        }
-        if constexpr (!DYN) {       // static: the first later clip of this worker in which this group owns a half-tile
-            for (int nb = c0.b + n_static; nb < a.B; nb += n_static) {
+        Stream s;
+        stream_open<kVC>(s, a, 0, first_clip, vrank);
+        // TMA target after (clip, step j): the next half-tile of the same clip, else the first half-tile of one of the next
+        // clips this worker is known to get (two ordinals ahead at most for a cluster, one for a flat CTA: anything further
+        // is fetched only after this very group has made progress) in which this group owns one.  Executed by ONE lane (the
+        // last warp to finish reading raw).  Returns false if the target is not known yet: the lane then OWES the copy and
+        // issues it when its own warp arrives at that half-tile (rare: short clips, the group idles anyway).
+        auto issue_next_tile = [&](const Stream& s0) -> bool {
+            if (s0.j + 1 < s0.n_my) {
+                tile_issue_tma(a, s0.cc, vrank + (s0.j + 1) * kVC, raw, bar_raw);
+                return true;
+            }
+#pragma unroll 1
+            for (int d = 1; d <= (FLAT ? 1 : 2); ++d) {
+                const int nb = queue_get(clipq, s0.ord + d, first_clip);
+                if (nb >= a.B) return true;                     // end of this worker's stream: nothing to load
                 const ClipCtx c2 = clip_ctx(a, nb);
                 if (c2.n_act > vrank) {
                     tile_issue_tma(a, c2, vrank, raw, bar_raw);
-                    break;
+                    return true;
                 }
             }
-            return true;
+            return false;
+        };
+        bool i_owe = false;                              // (lane 0) this warp must issue the copy of the half-tile it is about to wait for
+        if (tg == 0 && s.valid) {
+            if (s.n_my > 0) tile_issue_tma(a, s.cc, vrank, raw, bar_raw);
+            else i_owe = !issue_next_tile(s);
         }
-#pragma unroll 1
-        for (int d = 1; d <= (FLAT ? 1 : 2); ++d) {
-            const int nb = queue_get(clipq, ord0 + d, first_clip);
-            if (nb >= a.B) return true;                     // end of this worker's stream: nothing to load
-            const ClipCtx c2 = clip_ctx(a, nb);
-            if (c2.n_act > vrank) {
-                tile_issue_tma(a, c2, vrank, raw, bar_raw);
-                return true;
-            }
-        }
-        return false;
-    };
-
-    // Phase bookkeeping: the n-th half-tile this group processes (n = 0, 1, ...) uses phase n of every barrier,
-    // i.e. parity n & 1.  A wait for phase n is only issued by a warp that has already arrived on phase n
-    // or whose own later work is needed to complete phase n+1, so the barrier is never more than one
-    // phase ahead of a waiter.
-    int fin_seq = 0;                         // clips whose output pass this warp has done; parity = slot of the exchange
-    int tnum = 0, prev_tnum = 0;             // ordinal of cur's / prev's half-tile among those of this group
-    bool i_owe = false;                      // (lane 0) this warp must issue the copy of the half-tile it is about to wait for
-    bool q_pending = false;                  // (cluster leader) an atomic is in flight: its result is published one iteration later
-    unsigned int q_val = 0;
-    int q_ord = 0;
-    if ((tid & (kGroupThreads - 1)) == 0 && cvalid) {
-        if (cn_my > 0) tile_issue_tma(a, cc, vrank, raw, bar_raw);
-        else i_owe = !issue_next_tile(0, cc, 0, 0);
-    }
-    float mx = 0.f;                          // running max of the mel power of the clip in flight (>= 0)
-    bool pend = false;                       // an output pass is owed (max delivered, not yet waited for)
-    int pend_b = 0, pend_n_my = 0;
-    int out_j = 0;                           // next retained half-tile of the pending clip to write out
-    bool have_max = false;                   // the pending clip's max has arrived (floor_v valid)
-    float floor_v = 0.f;
-
-    while (cvalid || pvalid || pend) {
-        const bool do_tile = cvalid && cj < cn_my;
-        const int ctile = vrank + cj * kVC;
-        // ---- Q: the leader fetches ahead (see "the clip queue") ------------------------------------------
-        if (leader) {
-            if (q_pending) {
-                const unsigned int c = static_cast<unsigned int>(a.n_workers) + q_val;
-                q_end = c >= static_cast<unsigned int>(a.B);
-                queue_put<FLAT, kCl>(clipq, q_ord, q_end ? kClipEnd : static_cast<int>(c));
-                q_pending = false;
-            }
-            if (cvalid && !q_end) {
-                if constexpr (FLAT) {
-                    const int steps_q = cn_my > 0 ? cn_my : 1;
-                    if (cj == (steps_q > 4 ? steps_q - 4 : 0)) {
-                        const int c = queue_fetch<true>(a, taken);
-                        ++taken;
-                        q_end = c == kClipEnd;
-                        queue_put<true, 1>(clipq, cord + 1, c);
-                    }
-                } else if (cj == 0) {
-                    q_val = atomicAdd(&a.queue->next, 1u);      // (not consumed in this iteration)
-                    q_ord = cord + 3;
-                    q_pending = true;
-                }
-            }
-        }
-        // ---- A: stage 1 ----------------------------------------------------------------------------
-        if (do_tile) {
-            if constexpr (DYN) {
+        // The n-th half-tile the group processes uses phase n of every barrier of the group, i.e. parity n & 1.
+        int tnum = 0;
+        while (s.valid) {
+            if (s.j < s.n_my) {
+                const int ctile = vrank + s.j * kVC;
                 if (lane == 0 && i_owe) {
-                    tile_issue_tma(a, cc, ctile, raw, bar_raw);
+                    tile_issue_tma(a, s.cc, ctile, raw, bar_raw);
                     i_owe = false;
                 }
-            }
-            mbar_wait(bar_raw, tnum & 1);
-            tile_fixup(a, cc, ctile, raw, grp, tid & (kGroupThreads - 1));
-            stage1(raw, Y, wv, wg, lane,
-                   [&]() {   // this warp is done with raw: the last of the 8 re-arms the TMA for the next half-tile
-                       __syncwarp();
-                       if (lane == 0) {
-                           __threadfence_block();
-                           const uint32_t old = atomicAdd(raw_readers, 1u);
-                           if (old == kGroupWarps - 1) {
-                               *raw_readers = 0;
+                mbar_wait(bar_raw, tnum & 1);
+                tile_fixup(a, s.cc, ctile, raw, grp, tg);
+                stage1(raw, Y, wv, wg, lane,
+                       [&]() {   // this warp is done with raw: the last of the 8 re-arms the TMA for the next half-tile
+                           __syncwarp();
+                           if (lane == 0) {
                                __threadfence_block();
-                               asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                               i_owe = !issue_next_tile(cord, cc, cn_my, cj);
+                               const uint32_t old = atomicAdd(raw_readers, 1u);
+                               if (old == kGroupWarps - 1) {
+                                   *raw_readers = 0;
+                                   __threadfence_block();
+                                   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                                   i_owe = !issue_next_tile(s);
+                               }
                            }
-                       }
-                   },
-                   [&]() {});
-            __syncwarp();      // Y is private to the warp: this is the whole stage 1 -> stage 2 hand-over
+                       },
+                       [&]() {});
+                __syncwarp();      // Y is private to the warp: this is the whole stage 1 -> stage 2 hand-over
+                stage2(Y, P, wg, lane, [&]() {
+                    // the back end must have read the previous half-tile's P
+                    if (tnum > 0) mbar_wait(bar_pfree, (tnum - 1) & 1);
+                });
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_pfull);   // phase tnum
+                ++tnum;
+            }
+            stream_advance<kVC>(s, a, clipq, first_clip, vrank);
         }
-        // ---- F: output of the clip that ended one step ago, ONE retained half-tile per step ----------------------
-        // (the slot the mel stage below is about to overwrite: tcgen05.ld is 64 B/clk per SM, so a whole-clip pass by
-        // all 16 warps at once stalls everything for ~4k cycles; spread over the next clip's steps it hides under the FFTs)
+    } else {
+        // ============================================================================================
+        // BACK END: warp bw serves group (bw & 3) >> 1 with kRunsPerBe of its 8 filter runs, lane = frame.  Per step:
+        //   F  output of the clip that ended before this one: ONE retained half-tile (the slot B is about to overwrite)
+        //   B  mel stage of the step's half-tile: wait P full | sparse gather | retain the mel power | arrive P free
+        //   D  the clip ended: warp max -> group max; the group's last back-end warp delivers it to all CTAs of the clip
+        // ============================================================================================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kBeRegs));
+        const int bw = warp - kFeWarps;
+        const int quarter = bw & 3;                      // TMEM lane quarter this warp may touch (= warp & 3)
+        const int grp = quarter >> 1;
+        const int W0 = (quarter & 1) * (kGroupWarps / 2) + (bw >> 2) * kRunsPerBe;      // first filter run of this warp
+        const int wcol0 = (bw >> 2) * kRunsPerBe * kTmemColsPerRun;                     // its first column inside a slot
+        const int vrank = rank * kGroups + grp;
+        unsigned char* gbase = smem + grp * kSmemGroup;
+        const float* P = reinterpret_cast<const float*>(gbase + kSmemRaw + kSmemY);
+        unsigned char* gm = misc + grp * 64;
+        const uint32_t bar_pfull = smem_u32(gm + 24), bar_pfree = smem_u32(gm + 32);
+        const uint32_t twin = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);  // lane i <-> frame i of the half-tile
+        const bool leader = vrank == 0 && bw == 0 && lane == 0;
+
+        Stream s;
+        stream_open<kVC>(s, a, 0, first_clip, vrank);
+        int taken = FLAT ? 1 : 2;                // (leader) clips this worker has been given so far
+        bool q_end = false;                      // (leader) the queue has answered "no more"
+        int tnum = 0;
+        int fin_seq = 0;                         // clips whose max this warp has taken; parity = slot of the exchange
+        float mx = 0.f;                          // running max of the mel power of the clip in flight (>= 0)
+        bool pend = false;                       // an output pass is owed (max delivered, not yet waited for)
+        int pend_b = 0, pend_n_my = 0, pend_n_act = 0;
+        int out_j = 0;                           // next retained half-tile of the pending clip to write out
+        bool have_max = false;                   // the pending clip's max has arrived (floor_v valid)
+        float floor_v = 0.f;
+
+        // rows [m0, m0 + nf) of run W, frame `lane` of half-tile `tile` of clip b: element index into a.out
+        auto row0 = [&](int b, int W, int tile) {
+            return (static_cast<int64_t>(b) * a.n_mels + kt.m0[W]) * kNFrames + tile * kTile + lane;
+        };
+        // F: one retained half-tile of the pending clip -> (max(log10 p, gmax - 8) + 4) / 4 -> HBM
         auto output_slot = [&](int j) {
-            constexpr float kLog10_2 = 0.30102999566398120f;
-            const int nf = kt.nf[wg];
-            float r[16];
-            tmem_wait_st();
-            tmem_ld_x16(twin + j * kTmemColsPerTile, r);
-            const int f0 = (vrank + j * kVC) * kTile;
-            const int64_t e0 = (static_cast<int64_t>(pend_b) * a.n_mels + kt.m0[wg]) * kNFrames + lane + f0;
-            const bool va = f0 + lane < kNFrames;
-            with_out_type<OutT>(a, [&](auto* outp) {
+            const int tile = vrank + j * kVC;
+            const bool va = tile * kTile + lane < kNFrames;
+            if constexpr (!FLAT) tmem_wait_st();
+            with_out_type(a, [&](auto* outp) {
                 using T = std::remove_pointer_t<decltype(outp)>;
-                T* of = outp + e0;
-                // rows in blocks of four: straight-line code inside a block, so four MUFU.LG2 chains overlap
+#pragma unroll 1
+                for (int r = 0; r < kRunsPerBe; ++r) {
+                    const int W = W0 + r, nf = kt.nf[W];
+                    T* of = outp + row0(pend_b, W, tile);
+                    if constexpr (FLAT) {
+                        // the rows this very thread wrote a few steps ago: clamp in place (thr is rounded like the features)
+                        const float thr = from_out<T>(to_out<T>(fmaf(floor_v, 0.25f, 1.0f)));
 #pragma unroll
-                for (int q0 = 0; q0 < kMaxFiltersPerWarp; q0 += 4) {
-                    if (q0 < nf) {
-                        float lg[4];
+                        for (int q0 = 0; q0 < kMaxFiltersPerWarp; q0 += 8) {
+                            if (q0 < nf && va) {
+                                T v[8];
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            lg[i] = fmaxf(lg2_approx(r[q0 + i]) * kLog10_2, floor_v);
-                            lg[i] = fmaf(lg[i], 0.25f, 1.0f);   // (x+4)/4, TF-FE:161
+                                for (int i = 0; i < 8; ++i)
+                                    if (q0 + i < nf) v[i] = __ldcg(of + (q0 + i) * kNFrames);
+#pragma unroll
+                                for (int i = 0; i < 8; ++i)
+                                    if (q0 + i < nf && from_out<T>(v[i]) < thr) of[(q0 + i) * kNFrames] = to_out<T>(thr);
+                            }
                         }
+                    } else {
+                        constexpr float kLog10_2 = 0.30102999566398120f;
+                        float p[kMaxFiltersPerWarp];
+                        tmem_ld_x16(twin + j * kTmemColsPerSlot + wcol0 + r * kTmemColsPerRun, p);
+                        // rows in blocks of four: straight-line code inside a block, so four MUFU.LG2 chains overlap
 #pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            if (va && q0 + i < nf) of[(q0 + i) * kNFrames] = to_out<T>(lg[i]);
+                        for (int q0 = 0; q0 < kMaxFiltersPerWarp; q0 += 4) {
+                            if (q0 < nf) {
+                                float lg[4];
+#pragma unroll
+                                for (int i = 0; i < 4; ++i)
+                                    lg[i] = fmaf(fmaxf(lg2_approx(p[q0 + i]) * kLog10_2, floor_v), 0.25f, 1.0f);   // TF-FE:158,161
+#pragma unroll
+                                for (int i = 0; i < 4; ++i)
+                                    if (va && q0 + i < nf) of[(q0 + i) * kNFrames] = to_out<T>(lg[i]);
+                            }
+                        }
                     }
                 }
             });
         };
-        if (!FLAT && pend) {
-            if (!have_max) {    // first step after the clip ended: the 12 maxima
+        auto output_step = [&]() {
+            if (!have_max) {    // first step after the clip ended: the maxima of all virtual CTAs of the clip
                 const int fpar = fin_seq & 1;
-                mbar_wait_cluster(bar_max + fpar * 8, (fin_seq >> 1) & 1);
-                float pmax = lane < kVCluster ? clip_max[fpar * kVCluster + lane] : 0.f;
+                if constexpr (FLAT) mbar_wait(bar_max + fpar * 8, (fin_seq >> 1) & 1);
+                else mbar_wait_cluster(bar_max + fpar * 8, (fin_seq >> 1) & 1);
+                float pmax = lane < kVC ? clip_max[fpar * kVCluster + lane] : 0.f;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) pmax = fmaxf(pmax, __shfl_xor_sync(0xffffffffu, pmax, o));
                 ++fin_seq;
                 have_max = true;
                 const float gmax = log10_floor(pmax);                 // TF-FE:157
                 floor_v = fmaxf(gmax - 8.0f, -10.0f);                 // TF-FE:158 (log-mel is never below -10)
-                if (vrank == 0 && (tid & (kGroupThreads - 1)) == 0 && a.gmax) a.gmax[pend_b] = gmax;
+                if (leader && a.gmax) a.gmax[pend_b] = gmax;
                 // half-tiles of mine that hold no real sample: log-mel is exactly -10 everywhere
-                const float silent = (floor_v + 4.0f) * 0.25f;
-                const int nf = kt.nf[wg];
-                const int64_t e0 = (static_cast<int64_t>(pend_b) * a.n_mels + kt.m0[wg]) * kNFrames + lane;
-                with_out_type<OutT>(a, [&](auto* outp) {
+                const float silent = fmaf(floor_v, 0.25f, 1.0f);
+                with_out_type(a, [&](auto* outp) {
                     using T = std::remove_pointer_t<decltype(outp)>;
-                    for (int tile = vrank + pend_n_my * kVCluster; tile < kTilesPerClip; tile += kVCluster) {
-                        T* of = outp + e0 + tile * kTile;
-                        if (tile * kTile + lane < kNFrames)
-                            for (int q = 0; q < nf; ++q) of[q * kNFrames] = to_out<T>(silent);
+                    for (int tile = vrank + pend_n_my * kVC; tile < kTilesPerClip; tile += kVC) {
+                        if (tile * kTile + lane < kNFrames) {
+                            for (int r = 0; r < kRunsPerBe; ++r) {
+                                const int W = W0 + r, nf = kt.nf[W];
+                                T* of = outp + row0(pend_b, W, tile);
+                                for (int q = 0; q < nf; ++q) of[q * kNFrames] = to_out<T>(silent);
+                            }
+                        }
                     }
                 });
             }
             if (out_j < pend_n_my) output_slot(out_j++);
             if (out_j >= pend_n_my) pend = false;
-        }
-        // ---- B: mel stage of the previous half-tile ---------------------------------------------------------
-        const bool clip_ends = pvalid && plast;
-        const bool mel_tile = pvalid && phas;
-        const int cpar = fin_seq & 1;            // F has run: this is the parity of the clip ending now
-        float wmax = 0.f;                        // this warp's max over the clip (valid when clip_ends)
-        if (mel_tile) {
-            mbar_wait(bar_pfull, prev_tnum & 1);
-            const uint32_t tcol = twin + pj * kTmemColsPerTile;
-            float m1;
-            if constexpr (FLAT) {
-                // no retention: (max(log10 p, -10) + 4) / 4 goes to HBM now, the max - 8 clamp follows when the clip is done
-                const int nf = kt.nf[wg];
-                const int64_t e0 = (static_cast<int64_t>(pb) * a.n_mels + kt.m0[wg]) * kNFrames + ptile * kTile + lane;
-                const bool va = ptile * kTile + lane < kNFrames;
-                auto sink = [&](const float (&o)[kMaxFiltersPerWarp]) {
-                    constexpr float kLog10_2 = 0.30102999566398120f;
-                    with_out_type<OutT>(a, [&](auto* outp) {
-                        using T = std::remove_pointer_t<decltype(outp)>;
-                        T* of = outp + e0;
-#pragma unroll
-                        for (int q = 0; q < kMaxFiltersPerWarp; ++q)
-                            if (q < nf && va) of[q * kNFrames] = to_out<T>(fmaf(fmaxf(lg2_approx(o[q]) * kLog10_2, -10.0f), 0.25f, 1.0f));
-                    });
-                };
-                m1 = NMELS == 0 ? mel_stage(kt, P, wg, lane, sink) : mel_fixed<NMELS == 0 ? 80 : NMELS>(kt, P, wg, lane, sink);
-            } else {
-                auto sink = [&](const float (&o)[kMaxFiltersPerWarp]) { tmem_st_x16(tcol, o); };
-                m1 = NMELS == 0 ? mel_stage(kt, P, wg, lane, sink) : mel_fixed<NMELS == 0 ? 80 : NMELS>(kt, P, wg, lane, sink);
+        };
+
+        while (s.valid || pend) {
+            const bool do_tile = s.valid && s.j < s.n_my;
+            if (pend) output_step();                                   // ---- F
+            if (leader && s.valid && !q_end) {                         // ---- Q: fetch ahead (schedule: see the clip queue)
+                const int steps = s.n_my > 0 ? s.n_my : 1;
+                if (s.j == (FLAT ? (steps > 4 ? steps - 4 : 0) : 0)) {
+                    const int c = queue_fetch<FLAT>(a, taken);
+                    ++taken;
+                    q_end = c == kClipEnd;
+                    queue_put<FLAT, kCl>(clipq, s.ord + (FLAT ? 1 : 2), c);
+                }
             }
-            if (ptile * kTile + lane < kNFrames) mx = fmaxf(mx, m1);     // frames past 3000 do not exist
-            if (clip_ends) {
-                wmax = mx;
+            if (do_tile) {                                             // ---- B
+                const int tile = vrank + s.j * kVC;
+                mbar_wait_relaxed(bar_pfull, tnum & 1);
+                float m1;
+                if constexpr (FLAT) {
+                    // no retention: (max(log10 p, -10) + 4) / 4 goes to HBM now, the max - 8 clamp follows in F
+                    const bool va = tile * kTile + lane < kNFrames;
+                    auto run = [&](int, int W, const float (&o)[kMaxFiltersPerWarp]) {
+                        const int nf = kt.nf[W];
+                        with_out_type(a, [&](auto* outp) {
+                            using T = std::remove_pointer_t<decltype(outp)>;
+                            T* of = outp + row0(s.b, W, tile);
+#pragma unroll
+                            for (int q = 0; q < kMaxFiltersPerWarp; ++q)
+                                if (q < nf && va) of[q * kNFrames] = to_out<T>(fmaf(log10_floor(o[q]), 0.25f, 1.0f));
+                        });
+                    };
+                    m1 = mel_be<NMELS>(kt, P, W0, lane, run);
+                } else {
+                    const uint32_t tcol = twin + s.j * kTmemColsPerSlot + wcol0;
+                    auto run = [&](int r, int, const float (&o)[kMaxFiltersPerWarp]) { tmem_st_x16(tcol + r * kTmemColsPerRun, o); };
+                    m1 = mel_be<NMELS>(kt, P, W0, lane, run);
+                }
+                if (tile * kTile + lane < kNFrames) mx = fmaxf(mx, m1);     // frames past 3000 do not exist
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_pfree);   // phase tnum
+                ++tnum;
+            }
+            const bool clip_ends = s.valid && s.j + 1 >= (s.n_my > 0 ? s.n_my : 1);
+            if (clip_ends) {                                           // ---- D
+                while (pend) output_step();      // (only when this clip had fewer half-tiles than the one before it)
+                float wmax = mx;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
                 mx = 0.f;
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_pfree);   // phase prev_tnum
-        }
-        // ---- D: the clip ended: warp max -> group max; the LAST warp of the group to get here delivers the group's
-        // max to all 6 CTAs (remote store + remote mbarrier arrive).  Nobody waits; the peers get a whole step of
-        // slack before anyone needs the result (F, next step).
-        if (FLAT && clip_ends) {
-            // The CTA's 16 warps meet (once per clip), take the clip's max and clamp the clip's features in place:
-            // they were written moments ago and come back from L2.  flat_max is a ring of three so that the slot of the
-            // clip after next can be cleared here without racing with anybody (its last readers arrived above, its next
-            // writers wait for this thread's next arrival).
-            const int slot3 = clip_seq % 3;
-            __threadfence();                                         // this lane's feature stores are visible device-wide
-            __syncwarp();
-            if (lane == 0) {
-                if (mel_tile) atomicMax(flat_max + slot3, __float_as_int(wmax));
-                mbar_arrive(bar_clip);
-            }
-            mbar_wait(bar_clip, clip_seq & 1);
-            const float gmax = log10_floor(__int_as_float(*reinterpret_cast<volatile int*>(flat_max + slot3)));   // TF-FE:157
-            const float thr = (fmaxf(gmax - 8.0f, -10.0f) + 4.0f) * 0.25f;                                        // TF-FE:158,161
-            if (tid == 0) {
-                flat_max[(clip_seq + 2) % 3] = 0;
-                if (a.gmax) a.gmax[pb] = gmax;
-            }
-            const int n_valid = min(kNFrames, pn_act * kTile);          // frames of half-tiles that hold real samples
-            with_out_type<OutT>(a, [&](auto* outp) {
-                using T = std::remove_pointer_t<decltype(outp)>;
-                constexpr int kPer = 16 / static_cast<int>(sizeof(T));  // elements per 16-byte vector (3000 % kPer == 0)
-                struct alignas(16) Vec { T e[kPer]; };
-                Vec* oc = reinterpret_cast<Vec*>(outp + static_cast<int64_t>(pb) * a.n_mels * kNFrames);
-                const T thr_t = to_out<T>(thr);                          // rounded like the features: max(round x, round t) = round max(x, t)
-                const float thr_f = from_out<T>(thr_t);
-                // eight 16-byte loads in flight per thread: the clip may have left L2 by now (the cluster kernel streams through it)
-                constexpr int kRow = kNFrames / kPer;
-                const int nv = a.n_mels * kRow;
-                for (int i0 = tid; i0 < nv; i0 += 8 * kThreads) {
-                    Vec v[8];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int i = i0 + u * kThreads;
-#pragma unroll
-                        for (int e = 0; e < kPer; ++e) v[u].e[e] = thr_t;     // silent half-tiles: exactly -10 everywhere -> thr
-                        if (i < nv && (i % kRow) * kPer < n_valid) {          // (n_valid: multiple of 32 or 3000)
-                            const float4 w = __ldcg(reinterpret_cast<const float4*>(oc + i));
-                            v[u] = *reinterpret_cast<const Vec*>(&w);
+                const int cpar = fin_seq & 1;            // F has run: this is the parity of the clip ending now
+                if (lane == 0) {
+                    int* gmx = grp_max + cpar * kGroups + grp;
+                    uint32_t* gct = grp_cnt + cpar * kGroups + grp;
+                    if (s.n_my > 0) atomicMax(gmx, __float_as_int(wmax));     // non-negative floats order like their bit patterns
+                    __threadfence_block();
+                    if (atomicAdd(gct, 1u) == kBePerGroup - 1) {
+                        __threadfence_block();
+                        const float m = __int_as_float(atomicExch(gmx, 0));  // (reset for the clip after next)
+                        atomicExch(gct, 0u);
+                        const uint32_t bar_l = bar_max + cpar * 8;
+                        if constexpr (FLAT) {
+                            clip_max[cpar * kVCluster + vrank] = m;
+                            mbar_arrive(bar_l);                          // (release: the store above is visible to the waiters)
+                        } else {
+                            // Fire-and-forget: st.async writes the value into the peer's clip_max and completes 4 bytes on the
+                            // peer's bar_max.  Every CTA's group 0 posts the expectation of kVC x 4 bytes.
+                            const uint32_t slot_l = smem_u32(clip_max + cpar * kVCluster + vrank);
+                            if (grp == 0) mbar_expect_tx(bar_l, 4u * kVC);
+                            for (int r = 0; r < kCl; ++r) {
+                                uint32_t slot_r, bar_r;
+                                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(slot_r) : "r"(slot_l), "r"(r));
+                                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(bar_r) : "r"(bar_l), "r"(r));
+                                asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
+                                             ::"r"(slot_r), "r"(__float_as_uint(m)), "r"(bar_r) : "memory");
+                            }
                         }
                     }
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int i = i0 + u * kThreads;
-#pragma unroll
-                        for (int e = 0; e < kPer; ++e)
-                            if (from_out<T>(v[u].e[e]) < thr_f) v[u].e[e] = thr_t;
-                        if (i < nv) *reinterpret_cast<float4*>(oc + i) = *reinterpret_cast<const float4*>(&v[u]);
-                    }
                 }
-            });
-            ++clip_seq;
-        }
-        if (!FLAT && clip_ends) {
-            while (pend) {      // (only when this clip had fewer half-tiles than the one before it: finish that one first)
-                if (out_j < pend_n_my) output_slot(out_j++);
-                if (out_j >= pend_n_my) pend = false;
+                pend = true;
+                have_max = false;
+                out_j = 0;
+                pend_b = s.b;
+                pend_n_my = s.n_my;
+                pend_n_act = s.cc.n_act;
             }
-            if (lane == 0) {
-                int* gmx = grp_max + cpar * kGroups + grp;
-                uint32_t* gct = grp_cnt + cpar * kGroups + grp;
-                if (mel_tile) atomicMax(gmx, __float_as_int(wmax));     // non-negative floats order like their bit patterns
-                __threadfence_block();
-                if (atomicAdd(gct, 1u) == kGroupWarps - 1) {
-                    __threadfence_block();
-                    const float m = __int_as_float(atomicExch(gmx, 0));  // (reset for the clip after next)
-                    atomicExch(gct, 0u);
-                    // Fire-and-forget: st.async writes the value into the peer's clip_max and completes 4 bytes on the
-                    // peer's bar_max (a remote store + release-arrive pair cost ~900 cycles EACH on the one warp the
-                    // whole group was then waiting for).  Every CTA's group 0 posts the expectation of 12 x 4 bytes.
-                    const uint32_t slot_l = smem_u32(clip_max + cpar * kVCluster + vrank), bar_l = bar_max + cpar * 8;
-                    if (grp == 0) mbar_expect_tx(bar_l, 4u * kVCluster);
-                    for (int r = 0; r < kCluster; ++r) {
-                        uint32_t slot_r, bar_r;
-                        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(slot_r) : "r"(slot_l), "r"(r));
-                        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(bar_r) : "r"(bar_l), "r"(r));
-                        asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
-                                     ::"r"(slot_r), "r"(__float_as_uint(m)), "r"(bar_r) : "memory");
-                    }
-                }
-            }
-            pend = true;
-            have_max = false;
-            out_j = 0;
-            pend_b = pb;
-            pend_n_my = pn_my;
+            if (s.valid) stream_advance<kVC>(s, a, clipq, first_clip, vrank);
         }
-        // ---- C: stage 2 (every warp, on its own two frame pairs) ------------------------------------------
-        if (do_tile) {
-            stage2(Y, P, wg, lane, [&]() {
-                // the mel stage of the previous half-tile must have read P (all warps of the group)
-                if (tnum > 0) mbar_wait(bar_pfree, (tnum - 1) & 1);
-            });
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_pfull);   // phase tnum
-        }
-        // this step becomes the previous one; advance to the next step of the stream
-        const int steps = cn_my > 0 ? cn_my : 1;
-        pvalid = cvalid; phas = do_tile; plast = cvalid && cj + 1 >= steps;
-        pb = cb; pj = cj; ptile = ctile; pn_my = cn_my; pn_act = cc.n_act;
-        prev_tnum = tnum;
-        if (do_tile) ++tnum;
-        if (cvalid) {
-            if (cj + 1 < steps) {
-                ++cj;
-            } else {
-                ++cord;
-                cb = DYN ? queue_get(clipq, cord, first_clip) : cb + n_static;
-                cj = 0;
-                cn_my = 0;
-                cvalid = cb < a.B;
-                if (cvalid) {
-                    cc = clip_ctx(a, cb);
-                    cn_my = my_tiles(cc.n_act);
-                }
-            }
-        }
+        (void)pend_n_act;
     }
     if constexpr (FLAT) {
-        // A programmatic dependent of the cluster kernel and the LAST kernel of the launch in the stream: it must not
-        // complete before the clusters have written everything, or later work in the stream (the copy of the features, the
-        // next launch) could overtake them.  The clusters raise a counter when their stores are out; one thread here waits
-        // for it (griddepcontrol.wait would do, but it also waits for the primary grid to drain and flush: +10 us per launch).
-        if (tid == 0) {
-            const volatile unsigned int* cd = &a.queue->clusters_done;
-            while (*cd < static_cast<unsigned int>(a.n_clusters)) __nanosleep(256);
-            __threadfence();
-        }
         __syncthreads();
-        if (tid == 0 && atomicAdd(&a.queue->flat_done, 1u) == static_cast<unsigned int>(a.n_flat_ctas) - 1u) {
-            a.queue->clusters_done = 0u;         // (the next launch starts after this kernel has completed)
-            a.queue->flat_done = 0u;
-            __threadfence();
-        }
+        // a programmatic dependent of the cluster kernel: completing only after it keeps later work in the stream (the copy
+        // of the features, the next launch) behind BOTH kernels
+        asm volatile("griddepcontrol.wait;" ::: "memory");
     } else {
         // all TMEM reads are complete (tcgen05.wait::ld inside tmem_ld_x16); release the allocation
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        if (a.n_flat_ctas > 0) __threadfence();      // this thread's feature stores are visible device-wide ...
         cluster.sync();   // also keeps every CTA's shared memory alive until its peers have delivered their last max
         if (warp == 0) tmem_dealloc_512(tmem_base);
-        if (a.n_flat_ctas > 0 && rank == 0 && tid == 0) atomicAdd(&a.queue->clusters_done, 1u);   // ... before the flat kernel may leave
     }
-    // (DYN) every warp of this worker is past its last fetch: the last worker of the launch leaves the queue at {0, 0}
-    if (leader) {
+    // every warp of this worker is past its last fetch: the last worker of the launch leaves the queue at {0, 0}
+    if (rank == 0 && tid == 0) {
         if (atomicAdd(&a.queue->done, 1u) == static_cast<unsigned int>(a.n_workers) - 1u) {
             a.queue->next = 0u;
             a.queue->done = 0u;
@@ -1133,26 +1105,15 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
 // ---- host side -----------------------------------------------------------------------------------
 // variant: 80 / 128 when the table's structure equals the baked one (and the partition was taken from it)
 typedef void (*KernelFn)(const ClipArgs, const KernelTables, const float*);
-template <class OutT, bool DYN>
-inline KernelFn kernel_for_t(int variant, bool flat) {
+inline KernelFn kernel_for(int variant, bool flat = false) {
     if (flat) {
-        if (variant == 80) return logmel_cluster_kernel<80, true, OutT, DYN>;
-        if (variant == 128) return logmel_cluster_kernel<128, true, OutT, DYN>;
-        return logmel_cluster_kernel<0, true, OutT, DYN>;
+        if (variant == 80) return logmel_cluster_kernel<80, true>;
+        if (variant == 128) return logmel_cluster_kernel<128, true>;
+        return logmel_cluster_kernel<0, true>;
     }
-    if (variant == 80) return logmel_cluster_kernel<80, false, OutT, DYN>;
-    if (variant == 128) return logmel_cluster_kernel<128, false, OutT, DYN>;
-    return logmel_cluster_kernel<0, false, OutT, DYN>;
-}
-inline KernelFn kernel_for(int variant, bool flat = false, int out_format = WLM_OUT_F32, bool dyn = false) {
-    if (dyn) {
-        if (out_format == WLM_OUT_BF16) return kernel_for_t<__nv_bfloat16, true>(variant, flat);
-        if (out_format == WLM_OUT_F16) return kernel_for_t<__half, true>(variant, flat);
-        return kernel_for_t<float, true>(variant, flat);
-    }
-    if (out_format == WLM_OUT_BF16) return kernel_for_t<__nv_bfloat16, false>(variant, flat);
-    if (out_format == WLM_OUT_F16) return kernel_for_t<__half, false>(variant, flat);
-    return kernel_for_t<float, false>(variant, flat);
+    if (variant == 80) return logmel_cluster_kernel<80, false>;
+    if (variant == 128) return logmel_cluster_kernel<128, false>;
+    return logmel_cluster_kernel<0, false>;
 }
 
 inline void fill_launch_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* at, int n_clusters, cudaStream_t st) {
@@ -1171,12 +1132,10 @@ inline void fill_launch_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* at,
 
 inline cudaError_t configure(int variant, int* max_clusters) {
     KernelFn fn = kernel_for(variant);
-    cudaError_t e = cudaSuccess;
-    for (int fmt : {WLM_OUT_F32, WLM_OUT_BF16, WLM_OUT_F16})
-        for (int k = 0; k < 4; ++k) {
-            e = cudaFuncSetAttribute(kernel_for(variant, (k & 1) != 0, fmt, (k & 2) != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-            if (e != cudaSuccess) return e;
-        }
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(kernel_for(variant, true), cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg;
     cudaLaunchAttribute at[1];
     fill_launch_config(&cfg, at, 148, nullptr);
@@ -1190,83 +1149,51 @@ inline cudaError_t configure(int variant, int* max_clusters) {
 
 // The flat kernel runs on the `flat_ctas` SMs the clusters leave idle.  Next to a running cluster kernel a flat CTA needs
 // about `rounds_per_clip` cluster rounds (one clip per co-resident cluster) for a clip (tools/flat_time.py), so it is only
-// worth starting -- and, in a dynamic launch, only worth taking another clip -- while the clusters still have at least that
-// many rounds of clips ahead of them; otherwise the whole GPU would wait for 16 SMs at the end of the batch.
-inline double flat_rounds_per_clip(int n_mels) { return 6.5 + 0.00625 * n_mels; }
+// worth starting -- and, inside the kernel, only worth taking another clip -- while the clusters still have at least that
+// many rounds of unassigned clips ahead of them; otherwise the whole GPU would wait for 16 SMs at the end of the batch.
 inline int flat_reserve_clips(int n_mels, int n_clusters) {
-    return static_cast<int>(flat_rounds_per_clip(n_mels) * n_clusters + 0.999);
-}
-// static split of a dense batch: the largest number of whole flat rounds (one clip per flat CTA) that finish no later
-// than the cluster kernel does with the rest
-inline int flat_clip_count(const ClipArgs& a, int max_clusters, int flat_ctas) {
-    if (flat_ctas <= 0 || a.B < 2 * max_clusters) return 0;
-    const double rounds_per_clip = flat_rounds_per_clip(a.n_mels);
-    int k = 0;
-    while ((k + 1) * flat_ctas < a.B &&
-           (k + 1) * rounds_per_clip <= (a.B - (k + 1) * flat_ctas + max_clusters - 1) / max_clusters) ++k;
-    return k * flat_ctas;
+    const double rounds_per_clip = 6.5 + 0.00625 * n_mels;
+    return static_cast<int>(rounds_per_clip * n_clusters + 0.999);
 }
 
-// One launch = the cluster kernel plus, when it pays, its flat twin, as a PROGRAMMATIC DEPENDENT launch: the flat kernel
-// becomes schedulable when every CTA of the cluster kernel has executed griddepcontrol.launch_dependents, i.e. is resident --
-// its CTAs can then only land on the SMs the clusters left free.  (Submitted as an independent kernel on a second stream it
-// sometimes got SMs first and kept clusters from being placed.)  It consumes nothing the cluster kernel produces; before
-// its CTAs leave they wait for the clusters' completion counter (ClipQueue::clusters_done), so the last kernel in the stream
-// completes after both have written everything and later work in the stream is ordered behind both.
-//   dense batch (no per-clip lengths), flat_override < 0:  STATIC -- clips [0, B - n_flat) round-robin over the clusters,
-//       the last n_flat over the flat CTAs (every clip costs the same, so the split is known up front and the kernels carry
-//       no queue code: the dynamic variant measured 6 % slower on dense batches);
-//   everything else:  DYNAMIC -- both kernels pull clips from the plan's queue.
-// flat_override: -1 = the rules above; 0 = no flat kernel; n > 0 = dynamic, the flat kernel may take up to n clips, no
-// reserve (tests: any assignment must give bit-identical features).
+// One launch = the cluster kernel over the whole batch plus, when it pays, its flat twin; both pull clips from the plan's
+// queue.  The flat kernel is a PROGRAMMATIC DEPENDENT launch: it becomes schedulable when every CTA of the cluster kernel has
+// executed griddepcontrol.launch_dependents, i.e. is resident -- its CTAs can then only land on the SMs the clusters left
+// free.  (Submitted as an independent kernel on a second stream it sometimes got SMs first and kept clusters from being
+// placed.)  It consumes nothing the cluster kernel produces; it executes griddepcontrol.wait just before it exits, so it
+// completes after the cluster kernel and later work in the stream is ordered behind both.
+// flat_override: -1 = the rule above; 0 = no flat kernel; n > 0 = the flat kernel may take up to n clips, no reserve
+// (tests: any assignment must give bit-identical features).
 inline cudaError_t launch(const ClipArgs& a0, const Tables* d_tables, const Tables& h_tables, int variant,
                           int max_clusters, cudaStream_t st, int* n_launches, int flat_ctas = 0, int flat_override = -1,
                           bool* flat_broken = nullptr) {
     ClipArgs a = a0;
-    const bool dyn = !(a.lengths == nullptr && flat_override < 0);
-    int nc, nf = 0;
-    ClipArgs af = a;
-    a.clip_first = 0;
-    a.worker_base = 0;
-    a.flat_reserve = 0;
+    const int nc = a.B < max_clusters ? a.B : max_clusters;
+    int nf = 0;
+    a.flat_reserve = flat_reserve_clips(a.n_mels, nc);
     a.flat_cap = 0x7fffffff;
-    if (!dyn) {
-        const int n_flat = flat_clip_count(a, max_clusters, flat_ctas);
-        af = a;
-        af.clip_first = a.B - n_flat;
-        a.B -= n_flat;
-        nc = a.B < max_clusters ? a.B : max_clusters;
-        nf = n_flat < flat_ctas ? n_flat : flat_ctas;
-        a.n_workers = nc;
-        af.n_workers = nf;
-    } else {
-        nc = a.B < max_clusters ? a.B : max_clusters;
-        a.flat_reserve = flat_reserve_clips(a.n_mels, nc);
-        if (flat_ctas > 0 && flat_override != 0) {
-            if (flat_override > 0) {
-                nf = flat_override < flat_ctas ? flat_override : flat_ctas;
-                if (nf > a.B - nc) nf = a.B - nc;
-                a.flat_reserve = 0;
-                a.flat_cap = nf > 0 ? (flat_override + nf - 1) / nf : 0;
-            } else {
-                nf = a.B - a.flat_reserve;
-                if (nf > flat_ctas) nf = flat_ctas;
-            }
-            if (nf < 0) nf = 0;
+    if (flat_ctas > 0 && flat_override != 0) {
+        if (flat_override > 0) {
+            nf = flat_override < flat_ctas ? flat_override : flat_ctas;
+            if (nf > a.B - nc) nf = a.B - nc;
+            a.flat_reserve = 0;
+            a.flat_cap = nf > 0 ? (flat_override + nf - 1) / nf : 0;
+        } else {
+            nf = a.B - a.flat_reserve;
+            if (nf > flat_ctas) nf = flat_ctas;
         }
-        a.n_workers = nc + nf;
-        af = a;
-        af.worker_base = nc;
+        if (nf < 0) nf = 0;
     }
-    a.n_clusters = af.n_clusters = nc;
-    a.n_flat_ctas = af.n_flat_ctas = nf;
+    a.n_workers = nc + nf;
+    a.worker_base = 0;
     cudaLaunchConfig_t cfg;
     cudaLaunchAttribute at[1];
     fill_launch_config(&cfg, at, nc, st);
     *n_launches = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel_for(variant, false, a.out_format, dyn), a, h_tables.mel,
-                                       static_cast<const float*>(d_tables->win_lane));
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel_for(variant), a, h_tables.mel, static_cast<const float*>(d_tables->win_lane));
     if (e != cudaSuccess || nf == 0) return e;
+    ClipArgs af = a;
+    af.worker_base = nc;
     cudaLaunchConfig_t fcfg;
     memset(&fcfg, 0, sizeof(fcfg));
     fcfg.gridDim = dim3(nf);
@@ -1279,8 +1206,7 @@ inline cudaError_t launch(const ClipArgs& a0, const Tables* d_tables, const Tabl
     fcfg.attrs = fat;
     fcfg.numAttrs = 1;
     *n_launches = 2;
-    e = cudaLaunchKernelEx(&fcfg, kernel_for(variant, true, af.out_format, dyn), af, h_tables.mel,
-                           static_cast<const float*>(d_tables->win_lane));
+    e = cudaLaunchKernelEx(&fcfg, kernel_for(variant, true), af, h_tables.mel, static_cast<const float*>(d_tables->win_lane));
     if (e == cudaSuccess) return e;
     // the dependent launch was refused (driver without programmatic launches?): the flat CTAs' clips are already theirs, so
     // the same kernel goes out as an ordinary launch (it then runs after the cluster kernel) and the plan stops using it
@@ -1288,8 +1214,7 @@ inline cudaError_t launch(const ClipArgs& a0, const Tables* d_tables, const Tabl
     if (flat_broken) *flat_broken = true;
     fcfg.attrs = nullptr;
     fcfg.numAttrs = 0;
-    return cudaLaunchKernelEx(&fcfg, kernel_for(variant, true, af.out_format, dyn), af, h_tables.mel,
-                              static_cast<const float*>(d_tables->win_lane));
+    return cudaLaunchKernelEx(&fcfg, kernel_for(variant, true), af, h_tables.mel, static_cast<const float*>(d_tables->win_lane));
 }
 
 }  // namespace fused

@@ -57,6 +57,7 @@ struct wlm_plan {
     MelSparse h_sparse;
     fused::Tables* d_fused_tables = nullptr;
     fused::Tables h_fused_tables;
+    ClipQueue* d_queue = nullptr;  // clip counter the two kernels of a launch pull from (self-resetting)
     int max_clusters = 0;          // co-resident clusters of the fused kernel (occupancy query)
     int flat_ctas = 0;             // SMs the clusters cannot cover: they run the flat kernel (programmatic dependent launch)
     int variant = 0;               // 80 / 128: unrolled mel stage (Whisper banks); 0: table-driven
@@ -171,6 +172,8 @@ extern "C" int wlm_plan_create(int device, int n_mels, const float* mel_dense_ho
         }
         WLM_CUDA_P(cudaMalloc(&p->d_fused_tables, sizeof(fused::Tables)));
         WLM_CUDA_P(cudaMemcpy(p->d_fused_tables, &p->h_fused_tables, sizeof(fused::Tables), cudaMemcpyHostToDevice));
+        WLM_CUDA_P(cudaMalloc(&p->d_queue, sizeof(ClipQueue)));
+        WLM_CUDA_P(cudaMemset(p->d_queue, 0, sizeof(ClipQueue)));
         cudaError_t fe = fused::configure(p->variant, &p->max_clusters);
         if (fe != cudaSuccess) {
             wlm_plan_destroy(p);
@@ -197,6 +200,7 @@ extern "C" int wlm_plan_destroy(wlm_plan* p) {
     cudaSetDevice(p->device);
     cudaDeviceSynchronize();
     cudaFree(p->d_fused_tables);
+    cudaFree(p->d_queue);
     cudaFree(p->d_stage); cudaFree(p->d_offsets); cudaFree(p->d_lengths); cudaFree(p->d_ws);
     for (auto& r : p->h_ring) if (r) cudaFreeHost(r);
     if (p->h_offsets) cudaFreeHost(p->h_offsets);
@@ -238,13 +242,18 @@ extern "C" size_t wlm_workspace_bytes(const wlm_plan* p, int B) {
 // ------------------------------------------------------------------------------------------
 // launch
 // ------------------------------------------------------------------------------------------
-static int launch_logmel(wlm_plan* p, const ClipArgs& a, cudaStream_t st) {
+static int launch_logmel(wlm_plan* p, const ClipArgs& a0, cudaStream_t st) {
     int n_launches = 0;
     bool flat_broken = false;
+    ClipArgs a = a0;
+    a.queue = p->d_queue;
     cudaError_t e = fused::launch(a, p->d_fused_tables, p->h_fused_tables, p->variant, p->max_clusters, st, &n_launches,
                                   p->flat_ctas, p->flat_override, &flat_broken);
     if (flat_broken) p->flat_ctas = 0;
-    if (e != cudaSuccess) return fail(WLM_ERR_CUDA, "fused launch failed: %s", cudaGetErrorString(e));
+    if (e != cudaSuccess) {
+        cudaMemsetAsync(p->d_queue, 0, sizeof(ClipQueue), st);      // whatever was launched has left: start clean next time
+        return fail(WLM_ERR_CUDA, "fused launch failed: %s", cudaGetErrorString(e));
+    }
     p->launches += n_launches;
     WLM_CUDA(cudaGetLastError());
     return WLM_OK;
@@ -285,7 +294,6 @@ extern "C" int wlm_logmel(wlm_plan* p, const void* pcm_dev, int pcm_format, cons
     a.pcm_format = pcm_format;
     a.n_mels = p->n_mels;
     a.B = B;
-    a.clip_first = 0;
     a.out = out_dev;
     a.gmax = gmax;
     a.out_format = p->out_format;
@@ -405,8 +413,7 @@ extern "C" int wlm_logmel_host(wlm_plan* p, const void* const* clips_host, const
         a.pcm_format = pcm_format;
         a.n_mels = p->n_mels;
         a.B = B;
-        a.clip_first = 0;
-        a.out = out_dev;
+            a.out = out_dev;
         a.gmax = static_cast<float*>(p->d_ws);
         a.out_format = p->out_format;
         int rc = launch_logmel(p, a, st);
@@ -490,8 +497,7 @@ extern "C" int wlm_logmel_host(wlm_plan* p, const void* const* clips_host, const
         a.pcm_format = pcm_format;
         a.n_mels = p->n_mels;
         a.B = b1 - b0;
-        a.clip_first = 0;
-        a.out = static_cast<char*>(out_dev) + (size_t)b0 * p->n_mels * kNFrames * out_elem_size(p);
+            a.out = static_cast<char*>(out_dev) + (size_t)b0 * p->n_mels * kNFrames * out_elem_size(p);
         a.gmax = static_cast<float*>(p->d_ws) + b0;
         a.out_format = p->out_format;
         int rc = launch_logmel(p, a, st);
