@@ -344,7 +344,7 @@ def make_workload(cx: Ctx, wl):
         torch.randn((B, N_SAMPLES), generator=g, out=host)
         host.mul_(0.1)
         w["pcm"] = host.to(cx.dev, non_blocking=True)
-        w["clips"] = [host[b].numpy() for b in range(B)]
+        w["clips"] = host.numpy()                      # dense host batch [B, 480000]: no per-clip Python work in the call
         w["true_audio_s"] = CLIP_SECONDS * B
         w["in_bytes"] = B * N_SAMPLES * 4
         w["lengths"] = w["offsets"] = None
@@ -359,8 +359,8 @@ def make_workload(cx: Ctx, wl):
         w["pcm"] = host.to(cx.dev, non_blocking=True)
         w["offsets"] = torch.from_numpy(offs).to(cx.dev)
         w["lengths"] = torch.from_numpy(lens.astype(np.int32)).to(cx.dev)
-        flat = host.numpy()
-        w["clips"] = [flat[o:o + n] for o, n in zip(offs, lens)]
+        w["clips"] = (host.numpy(), offs, np.minimum(lens, 2 ** 31 - 1).astype(np.int32))   # (buffer, offsets, lengths)
+        w["host_offsets"] = offs
         w["true_audio_s"] = float(np.minimum(lens, N_SAMPLES).sum()) / 16000.0
         w["in_bytes"] = int(np.minimum(lens, N_SAMPLES).sum()) * 4
     w["host"] = host
@@ -387,19 +387,16 @@ def measure(cx: Ctx, w, steps, warmup, e2e=True, e2e_extra=False):
     sampler = ClockSampler(visible_nvml_index(cx.local_rank))
     sampler.start()
     launches0 = fe.launch_count
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
     for s in range(steps):
-        evs[s][0].record()
         run_device()
-        evs[s][1].record()
     t1.record()
     cx.barrier()
     clocks = sampler.stop()
     launches = fe.launch_count - launches0
     dev_ms = t0.elapsed_time(t1)
-    launch_ms = sum(a.elapsed_time(b) for a, b in evs) / steps
+    launch_ms = dev_ms / steps        # back-to-back launches between two events on the launch stream: the average step
 
     # ---- end to end: pinned host PCM -> H2D -> kernels -> D2H of one float per clip --------------
     res = {}
@@ -445,11 +442,7 @@ def measure(cx: Ctx, w, steps, warmup, e2e=True, e2e_extra=False):
         h16 = torch.empty((w["host"].numel(),), dtype=torch.int16).pin_memory()
         h16.copy_((w["host"].reshape(-1) * 32767.0).round().to(torch.int16))
         a16 = h16.numpy()
-        if w["offsets"] is None:
-            c16 = [a16[b * N_SAMPLES:(b + 1) * N_SAMPLES] for b in range(B)]
-        else:
-            offs = w["offsets"].cpu().numpy()
-            c16 = [a16[o:o + c.shape[0]] for o, c in zip(offs, clips)]
+        c16 = a16.reshape(B, N_SAMPLES) if w["offsets"] is None else (a16, clips[1], clips[2])
 
         def e2e16_step():
             fe.extract_host(c16, out=out)

@@ -588,3 +588,27 @@ def test_pcm_dataset_items_through_the_device_collator(fe):
         assert batch["labels"].shape[0] == len(rows) and batch["bias_spans"].dim() == 3
         if name == "desc":
             assert (batch["labels"][:, 0] == -100).all()        # the prompt is masked up to <|startoftranscript|>
+
+
+def test_host_batch_forms_agree(fe):
+    """extract_host takes a list of 1-D arrays (what a dataset yields), a dense 2-D array, or (buffer, offsets, lengths);
+    the last two need no per-clip Python work.  All three must give the same bits."""
+    import torch
+
+    ex = fe[80]
+    rng = np.random.default_rng(31)
+    lens = rng.integers(0, 60000, size=17)
+    lens[3] = 0
+    offs = np.zeros(17, dtype=np.int64)
+    offs[1:] = np.cumsum((lens[:-1] + 7) // 8 * 8)
+    buf = (0.1 * rng.standard_normal(int(offs[-1] + lens[-1] + 8))).astype(np.float32)
+    as_list = [buf[o:o + n] for o, n in zip(offs, lens)]
+    a = ex.extract_host(as_list)
+    b = ex.extract_host((buf, offs, lens))
+    assert torch.equal(a, b)
+    dense = (0.1 * rng.standard_normal((5, 48000))).astype(np.float32)
+    c = ex.extract_host([dense[i] for i in range(5)])
+    d = ex.extract_host(dense)
+    assert torch.equal(c, d)
+    with pytest.raises(ValueError):
+        ex.extract_host((buf, offs, lens + 10 ** 6))

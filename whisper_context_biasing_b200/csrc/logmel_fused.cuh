@@ -1097,28 +1097,19 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
         }
     }
     if constexpr (FLAT) {
+        __syncthreads();
         // A programmatic dependent of the cluster kernel and the LAST kernel of the launch in the stream: it must not
         // complete before the clusters have written everything, or later work in the stream (the copy of the features, the
-        // next launch) could overtake them.  The clusters raise a counter when their stores are out; one thread here waits
-        // for it (griddepcontrol.wait would do, but it also waits for the primary grid to drain and flush: +10 us per launch).
-        if (tid == 0) {
-            const volatile unsigned int* cd = &a.queue->clusters_done;
-            while (*cd < static_cast<unsigned int>(a.n_clusters)) __nanosleep(256);
-            __threadfence();
-        }
-        __syncthreads();
-        if (tid == 0 && atomicAdd(&a.queue->flat_done, 1u) == static_cast<unsigned int>(a.n_flat_ctas) - 1u) {
-            a.queue->clusters_done = 0u;         // (the next launch starts after this kernel has completed)
-            a.queue->flat_done = 0u;
-            __threadfence();
-        }
+        // next launch) could overtake them.  The price is a second completion hop at the end of every launch (+10 us:
+        // round 1 lacked the wait and was that much faster per launch -- and wrong).  Measured alternatives: a completion
+        // counter polled here (+1 % on top), the flat kernel launched FIRST as the primary of the pair (its CTAs then
+        // take SMs the clusters need: +55 %).
+        asm volatile("griddepcontrol.wait;" ::: "memory");
     } else {
         // all TMEM reads are complete (tcgen05.wait::ld inside tmem_ld_x16); release the allocation
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        if (a.n_flat_ctas > 0) __threadfence();      // this thread's feature stores are visible device-wide ...
         cluster.sync();   // also keeps every CTA's shared memory alive until its peers have delivered their last max
         if (warp == 0) tmem_dealloc_512(tmem_base);
-        if (a.n_flat_ctas > 0 && rank == 0 && tid == 0) atomicAdd(&a.queue->clusters_done, 1u);   // ... before the flat kernel may leave
     }
     // (DYN) every warp of this worker is past its last fetch: the last worker of the launch leaves the queue at {0, 0}
     if (leader) {
@@ -1210,9 +1201,9 @@ inline int flat_clip_count(const ClipArgs& a, int max_clusters, int flat_ctas) {
 // One launch = the cluster kernel plus, when it pays, its flat twin, as a PROGRAMMATIC DEPENDENT launch: the flat kernel
 // becomes schedulable when every CTA of the cluster kernel has executed griddepcontrol.launch_dependents, i.e. is resident --
 // its CTAs can then only land on the SMs the clusters left free.  (Submitted as an independent kernel on a second stream it
-// sometimes got SMs first and kept clusters from being placed.)  It consumes nothing the cluster kernel produces; before
-// its CTAs leave they wait for the clusters' completion counter (ClipQueue::clusters_done), so the last kernel in the stream
-// completes after both have written everything and later work in the stream is ordered behind both.
+// sometimes got SMs first and kept clusters from being placed.)  It consumes nothing the cluster kernel produces; it
+// executes griddepcontrol.wait just before it exits, so the last kernel in the stream completes after both have written
+// everything and later work in the stream is ordered behind both.
 //   dense batch (no per-clip lengths), flat_override < 0:  STATIC -- clips [0, B - n_flat) round-robin over the clusters,
 //       the last n_flat over the flat CTAs (every clip costs the same, so the split is known up front and the kernels carry
 //       no queue code: the dynamic variant measured 6 % slower on dense batches);
@@ -1258,8 +1249,6 @@ inline cudaError_t launch(const ClipArgs& a0, const Tables* d_tables, const Tabl
         af = a;
         af.worker_base = nc;
     }
-    a.n_clusters = af.n_clusters = nc;
-    a.n_flat_ctas = af.n_flat_ctas = nf;
     cudaLaunchConfig_t cfg;
     cudaLaunchAttribute at[1];
     fill_launch_config(&cfg, at, nc, st);

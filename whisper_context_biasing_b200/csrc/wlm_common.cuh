@@ -28,14 +28,9 @@ struct MelSparse {
 // Work queue shared by the cluster kernel and its cluster-less twin (one per plan, device memory): the first
 // `n_workers` clips are taken statically, one per worker; every further clip is `n_workers + next++`.  The last worker to
 // leave resets both counters, so a launch always starts from {0, 0}.
-// `clusters_done` / `flat_done` order the two kernels of a launch: the flat kernel (a programmatic dependent launch, the
-// LAST kernel in the stream) must not complete before the cluster kernel has written everything, or later work in the
-// stream could overtake the clusters; its CTAs wait for `clusters_done == n_clusters` before they leave.
 struct ClipQueue {
     unsigned int next;
     unsigned int done;
-    unsigned int clusters_done;
-    unsigned int flat_done;
 };
 
 // Arguments common to every log-mel kernel launch.
@@ -54,8 +49,6 @@ struct ClipArgs {
     int32_t worker_base;      // index of this kernel's first worker: 0 (cluster kernel), number of clusters (flat kernel)
     int32_t flat_reserve;     // a flat CTA takes another clip only while at least this many clips are still unassigned
     int32_t flat_cap;         // clips a flat CTA may take at most
-    int32_t n_clusters;       // clusters of the launch's cluster kernel
-    int32_t n_flat_ctas;      // CTAs of its flat twin (0: no flat kernel in this launch)
     void* out;                // [B][n_mels][3000], element type out_format
     float* gmax;              // [B] (may be workspace)
     int32_t out_format;       // WLM_OUT_*

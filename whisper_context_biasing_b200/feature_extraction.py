@@ -281,32 +281,52 @@ class B200WhisperFeatureExtractor:
                                              C.c_void_p(mask.data_ptr()), self._stream()))
         return mask
 
-    def extract_host(self, clips: Sequence[np.ndarray], out=None, out_host=None):
-        """Host PCM (list of 1-D float32 or int16 numpy arrays, any lengths) -> features in HBM
-        through the plan's pinned H2D pipeline (wlm_logmel_host)."""
+    def extract_host(self, clips, out=None, out_host=None):
+        """Host PCM -> features in HBM through the plan's pinned H2D pipeline (wlm_logmel_host).
+
+        clips   a list of 1-D float32 / int16 numpy arrays of any lengths (what a dataset yields), or -- without any
+                per-clip Python work -- a C-contiguous 2-D array [B, L] (dense batch), or a tuple
+                (buffer, offsets, lengths): one 1-D array holding every clip, int64 element offsets and lengths."""
         import torch
 
-        B = len(clips)
+        keep = clips
+        if isinstance(clips, tuple) and len(clips) == 3 and isinstance(clips[0], np.ndarray):
+            buf, offs, lens_np = clips
+            if buf.ndim != 1 or not buf.flags["C_CONTIGUOUS"]:
+                raise ValueError("ragged host input: the buffer must be a C-contiguous 1-D array")
+            dt, B = buf.dtype, int(len(offs))
+            offs = np.asarray(offs, dtype=np.int64)
+            lens_arr = np.ascontiguousarray(lens_np, dtype=np.int32)
+            if B and (offs.min() < 0 or int((offs + lens_arr).max()) > buf.shape[0] or lens_arr.min() < 0):
+                raise ValueError("ragged host input: a clip lies outside the buffer")
+            ptr_arr = (buf.ctypes.data + offs * buf.itemsize).astype(np.uintp)
+        elif isinstance(clips, np.ndarray) and clips.ndim == 2:
+            if not clips.flags["C_CONTIGUOUS"]:
+                clips = keep = np.ascontiguousarray(clips)
+            dt, B = clips.dtype, clips.shape[0]
+            ptr_arr = (clips.ctypes.data + np.arange(B, dtype=np.int64) * clips.strides[0]).astype(np.uintp)
+            lens_arr = np.full((B,), clips.shape[1], dtype=np.int32)
+        else:
+            B = len(clips)
+            if B == 0:
+                return torch.empty((0, self.feature_size, self.nb_max_frames), dtype=self.feature_dtype, device=self.device)
+            dt = clips[0].dtype
+            if any(x.dtype != dt or x.ndim != 1 for x in clips):
+                raise ValueError("all clips must be 1-D arrays of the same dtype")
+            if not all(x.flags.c_contiguous for x in clips):
+                clips = keep = [np.ascontiguousarray(x) for x in clips]
+            ptr_arr = np.fromiter((x.__array_interface__["data"][0] for x in clips), dtype=np.uintp, count=B)
+            lens_arr = np.fromiter((x.shape[0] for x in clips), dtype=np.int32, count=B)
         if B == 0:
             return torch.empty((0, self.feature_size, self.nb_max_frames), dtype=self.feature_dtype, device=self.device)
-        dt = clips[0].dtype
         if dt == np.float32:
             fmt = N.WLM_PCM_F32
         elif dt == np.int16:
             fmt = N.WLM_PCM_I16
         else:
             raise ValueError(f"host PCM dtype {dt} not supported (float32 or int16)")
-        ptrs = (C.c_void_p * B)()
-        lens = (C.c_int32 * B)()
-        keep = []
-        for b, x in enumerate(clips):
-            if x.dtype != dt or x.ndim != 1:
-                raise ValueError("all clips must be 1-D arrays of the same dtype")
-            if not x.flags["C_CONTIGUOUS"]:
-                x = np.ascontiguousarray(x)
-            keep.append(x)
-            ptrs[b] = x.ctypes.data if x.shape[0] else None
-            lens[b] = x.shape[0]
+        ptrs = ptr_arr.ctypes.data_as(C.POINTER(C.c_void_p))
+        lens = lens_arr.ctypes.data_as(C.POINTER(C.c_int32))
         if out is None:
             out = torch.empty((B, self.feature_size, self.nb_max_frames), dtype=self.feature_dtype, device=self.device)
         else:
@@ -321,6 +341,7 @@ class B200WhisperFeatureExtractor:
             N.check(N.LIB.wlm_logmel_host(
                 self._plan, ptrs, lens, fmt, B, C.c_void_p(out.data_ptr()),
                 C.c_void_p(out_host.ctypes.data) if out_host is not None else None, self._stream()))
+        del keep, ptr_arr, lens_arr
         return out
 
     # -- the reference-facing call (TF-FE:189-342) ---------------------------------------------
