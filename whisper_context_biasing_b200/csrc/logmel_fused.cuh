@@ -858,21 +858,21 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
             }
             mbar_wait(bar_raw, tnum & 1);
             tile_fixup(a, cc, ctile, raw, grp, tid & (kGroupThreads - 1));
-            stage1(raw, Y, wv, wg, lane,
-                   [&]() {   // this warp is done with raw: the last of the 8 re-arms the TMA for the next half-tile
+            // This warp is done with raw once the 25-point DFTs have consumed its samples (the loads have then completed by
+            // data dependence, so no fence holds the warp up between its loads and its arithmetic); the last of the 8
+            // re-arms the TMA for the next half-tile, which is not needed before the next step.
+            stage1(raw, Y, wv, wg, lane, [&]() {},
+                   [&]() {
                        __syncwarp();
                        if (lane == 0) {
-                           __threadfence_block();
                            const uint32_t old = atomicAdd(raw_readers, 1u);
                            if (old == kGroupWarps - 1) {
                                *raw_readers = 0;
-                               __threadfence_block();
                                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                                i_owe = !issue_next_tile(cord, cc, cn_my, cj);
                            }
                        }
-                   },
-                   [&]() {});
+                   });
             __syncwarp();      // Y is private to the warp: this is the whole stage 1 -> stage 2 hand-over
         }
         // ---- F: output of the clip that ended one step ago, ONE retained half-tile per step ----------------------
@@ -1121,9 +1121,10 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
     }
 }
 
+typedef void (*KernelFn)(const ClipArgs, const KernelTables, const float*);
+#ifndef WLM_DEVICE_ONLY   /* tools/stream_ko.cu compiles one kernel, not the whole family */
 // ---- host side -----------------------------------------------------------------------------------
 // variant: 80 / 128 when the table's structure equals the baked one (and the partition was taken from it)
-typedef void (*KernelFn)(const ClipArgs, const KernelTables, const float*);
 template <class OutT, bool DYN>
 inline KernelFn kernel_for_t(int variant, bool flat) {
     if (flat) {
@@ -1280,6 +1281,8 @@ inline cudaError_t launch(const ClipArgs& a0, const Tables* d_tables, const Tabl
     return cudaLaunchKernelEx(&fcfg, kernel_for(variant, true, af.out_format, dyn), af, h_tables.mel,
                               static_cast<const float*>(d_tables->win_lane));
 }
+
+#endif  // WLM_DEVICE_ONLY
 
 }  // namespace fused
 }  // namespace wlm
