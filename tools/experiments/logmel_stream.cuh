@@ -23,7 +23,7 @@
 //
 // Shared memory (bytes):  raw 2 x 22,400 | Y 8 x 6,784 | P 3 x 26,752 | mbarriers + scratch 1024  = 180,352
 #pragma once
-#include "logmel_fused.cuh"
+#include "logmel_fused.cuh"   /* -I whisper_context_biasing_b200/csrc */
 
 namespace wlm {
 namespace stream {

@@ -21,6 +21,12 @@
 // (max(log10(max(p,1e-10)), gmax - 8) + 4) / 4 -- the features touch HBM exactly once.
 //
 // Shared memory (bytes):  raw 2 x 22,400 | Y 2 x 54,272 | P 2 x 26,752 | mbarriers + scratch 1024
+//
+// Template parameters of the kernel: NMELS (80 / 128: mel stage unrolled with the structure of that Whisper bank; 0: table-
+// driven), FLAT (the cluster-less twin for the SMs clusters cannot cover), OutT (float / bfloat16 / half feature store), DYN
+// (clips from the queue both kernels share -- ragged batches -- or a static split -- dense batches).
+// Two restructurings of this kernel were built and measured in round 2 and are NOT used (tools/experiments/, DESIGN.md
+// section 4): warp-specialised FFT / mel+output warps, and a streaming variant with multi-buffered raw and P.
 #pragma once
 #include <cooperative_groups.h>
 #include <cuda_bf16.h>
