@@ -64,6 +64,14 @@ using fused::vadd; using fused::vsub; using fused::vmul; using fused::vfma; usin
 namespace wlm {
 namespace fused {
 
+// Knock-outs for tools/fused_ko.cu (TIMING ONLY, results are wrong with any of them): 1 no raw wait / TMA re-arm, 2 no
+// wait for "P full", 4 no wait for "P free", 8 no mel arithmetic, 16 no output pass.  0 in every product build.
+#ifndef WLM_KO
+#define WLM_KO 0
+#endif
+constexpr bool kKoRaw = (WLM_KO & 1) != 0, kKoPfull = (WLM_KO & 2) != 0, kKoPfree = (WLM_KO & 4) != 0,
+               kKoMel = (WLM_KO & 8) != 0, kKoOut = (WLM_KO & 16) != 0;
+
 constexpr int kGroups = 2;                // independent warp groups per CTA
 constexpr int kGroupWarps = 8;
 constexpr int kGroupThreads = kGroupWarps * 32;
@@ -816,7 +824,7 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
     bool q_pending = false;                  // (cluster leader) an atomic is in flight: its result is published one iteration later
     unsigned int q_val = 0;
     int q_ord = 0;
-    if ((tid & (kGroupThreads - 1)) == 0 && cvalid) {
+    if ((tid & (kGroupThreads - 1)) == 0 && cvalid && !kKoRaw) {
         if (cn_my > 0) tile_issue_tma(a, cc, vrank, raw, bar_raw);
         else i_owe = !issue_next_tile(0, cc, 0, 0);
     }
@@ -862,7 +870,7 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
                     i_owe = false;
                 }
             }
-            mbar_wait(bar_raw, tnum & 1);
+            if constexpr (!kKoRaw) mbar_wait(bar_raw, tnum & 1);
             tile_fixup(a, cc, ctile, raw, grp, tid & (kGroupThreads - 1));
             // This warp is done with raw once the 25-point DFTs have consumed its samples (the loads have then completed by
             // data dependence, so no fence holds the warp up between its loads and its arithmetic); the last of the 8
@@ -875,7 +883,7 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
                            if (old == kGroupWarps - 1) {
                                *raw_readers = 0;
                                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                               i_owe = !issue_next_tile(cord, cc, cn_my, cj);
+                               if constexpr (!kKoRaw) i_owe = !issue_next_tile(cord, cc, cn_my, cj);
                            }
                        }
                    });
@@ -938,7 +946,7 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
                     }
                 });
             }
-            if (out_j < pend_n_my) output_slot(out_j++);
+            if (out_j < pend_n_my) { if constexpr (!kKoOut) output_slot(out_j); ++out_j; }
             if (out_j >= pend_n_my) pend = false;
         }
         // ---- B: mel stage of the previous half-tile ---------------------------------------------------------
@@ -947,7 +955,7 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
         const int cpar = fin_seq & 1;            // F has run: this is the parity of the clip ending now
         float wmax = 0.f;                        // this warp's max over the clip (valid when clip_ends)
         if (mel_tile) {
-            mbar_wait(bar_pfull, prev_tnum & 1);
+            if constexpr (!kKoPfull) mbar_wait(bar_pfull, prev_tnum & 1);
             const uint32_t tcol = twin + pj * kTmemColsPerTile;
             float m1;
             if constexpr (FLAT) {
@@ -968,7 +976,8 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
                 m1 = NMELS == 0 ? mel_stage(kt, P, wg, lane, sink) : mel_fixed<NMELS == 0 ? 80 : NMELS>(kt, P, wg, lane, sink);
             } else {
                 auto sink = [&](const float (&o)[kMaxFiltersPerWarp]) { tmem_st_x16(tcol, o); };
-                m1 = NMELS == 0 ? mel_stage(kt, P, wg, lane, sink) : mel_fixed<NMELS == 0 ? 80 : NMELS>(kt, P, wg, lane, sink);
+                if constexpr (kKoMel) m1 = P[lane];
+                else m1 = NMELS == 0 ? mel_stage(kt, P, wg, lane, sink) : mel_fixed<NMELS == 0 ? 80 : NMELS>(kt, P, wg, lane, sink);
             }
             if (ptile * kTile + lane < kNFrames) mx = fmaxf(mx, m1);     // frames past 3000 do not exist
             if (clip_ends) {
@@ -1075,7 +1084,7 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
         if (do_tile) {
             stage2(Y, P, wg, lane, [&]() {
                 // the mel stage of the previous half-tile must have read P (all warps of the group)
-                if (tnum > 0) mbar_wait(bar_pfree, (tnum - 1) & 1);
+                if constexpr (!kKoPfree) if (tnum > 0) mbar_wait(bar_pfree, (tnum - 1) & 1);
             });
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_pfull);   // phase tnum
