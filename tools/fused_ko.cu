@@ -47,7 +47,7 @@ int main(int argc, char** argv) {
     fused::Tables* d;
     CK(cudaMalloc(&d, sizeof(h))); CK(cudaMemcpy(d, &h, sizeof(h), cudaMemcpyHostToDevice));
     float *pcm, *out, *gmax;
-    CK(cudaMalloc(&pcm, (size_t)B * 480000 * 4)); CK(cudaMalloc(&out, (size_t)B * M * 3000 * 4)); CK(cudaMalloc(&gmax, B * 4));
+    CK(cudaMalloc(&pcm, (size_t)B * 480000 * 4)); CK(cudaMalloc(&out, (size_t)B * M * 3000 * 4)); CK(cudaMalloc(&gmax, (size_t)(B + 148 * 16 * 8) * 4));
     std::vector<float> hp(480000);
     for (int i = 0; i < 480000; ++i) hp[i] = 0.1f * sinf(0.37f * i) + 0.05f * sinf(0.011f * i * i * 1e-3f);
     for (int b = 0; b < B; ++b) CK(cudaMemcpy(pcm + (size_t)b * 480000, hp.data(), 480000 * 4, cudaMemcpyHostToDevice));
@@ -77,5 +77,23 @@ int main(int argc, char** argv) {
     const double us = ms * 100.0, rounds = (double)B / maxc;
     printf("%s: B=%d clusters=%d: %.1f us per launch, %.2f us per round, %.0f cycles per 64 frames per SM (at 1.965 GHz)\n",
            argv[0], B, maxc, us, us / rounds, us / rounds / 8.0 * 1965.0);
+#ifdef WLM_WAITSTAT
+    {   // cycles per warp in each kind of wait, averaged over the warps of the launch (last launch)
+        const int nw = (int)cfg.gridDim.x * 16;
+        std::vector<float> ws((size_t)nw * 8);
+        CK(cudaMemcpy(ws.data(), gmax, ws.size() * 4, cudaMemcpyDeviceToHost));
+        double acc[5] = {0, 0, 0, 0, 0};
+        for (int w = 0; w < nw; ++w) for (int k = 0; k < 5; ++k) acc[k] += ws[(size_t)w * 8 + k];
+        printf("  mean cycles per warp: loop %.0f | wait raw %.0f (%.1f%%) P full %.0f (%.1f%%) P free %.0f (%.1f%%) clip maxima %.0f (%.1f%%)\n",
+               acc[4] / nw, acc[0] / nw, 100 * acc[0] / acc[4], acc[1] / nw, 100 * acc[1] / acc[4], acc[2] / nw, 100 * acc[2] / acc[4],
+               acc[3] / nw, 100 * acc[3] / acc[4]);
+        for (int g = 0; g < 16; ++g) {      // by warp index inside the CTA (8 warps per group)
+            double a5[5] = {0, 0, 0, 0, 0};
+            for (int c = 0; c < (int)cfg.gridDim.x; ++c) for (int k = 0; k < 5; ++k) a5[k] += ws[((size_t)c * 16 + g) * 8 + k];
+            printf("  warp %2d: raw %5.1f%%  P full %5.1f%%  P free %5.1f%%  maxima %5.1f%%\n", g, 100 * a5[0] / a5[4], 100 * a5[1] / a5[4],
+                   100 * a5[2] / a5[4], 100 * a5[3] / a5[4]);
+        }
+    }
+#endif
     return 0;
 }

@@ -72,6 +72,18 @@ namespace fused {
 constexpr bool kKoRaw = (WLM_KO & 1) != 0, kKoPfull = (WLM_KO & 2) != 0, kKoPfree = (WLM_KO & 4) != 0,
                kKoMel = (WLM_KO & 8) != 0, kKoOut = (WLM_KO & 16) != 0;
 
+// -DWLM_WAITSTAT (tools/fused_ko.cu only): every warp accumulates the cycles it spends in each kind of wait and leaves them
+// in a.gmax[(cta * 16 + warp) * 8 + {0 raw, 1 P full, 2 P free, 3 clip maxima, 4 whole loop}]
+#ifdef WLM_WAITSTAT
+#define WLM_WS_BEGIN() const long long ws_t0 = clock64()
+#define WLM_WS_END(k) ws_acc[k] += clock64() - ws_t0
+#else
+#define WLM_WS_BEGIN()
+#define WLM_WS_END(k)
+#endif
+#ifndef WLM_OPAQUE_BASE
+#define WLM_OPAQUE_BASE 1
+#endif
 constexpr int kGroups = 2;                // independent warp groups per CTA
 constexpr int kGroupWarps = 8;
 constexpr int kGroupThreads = kGroupWarps * 32;
@@ -101,7 +113,15 @@ constexpr int kPRows = fft::kNumSlots * 16;                    // 208 (201 disti
 constexpr int kPPair = kPRows + (kPairs == 16 ? 1 : 2);        // 209 (= 1 mod 16) / 210 (8 pairs: 4 x 210 = 8 mod 16)
 constexpr int kPFloats = 2 * kPairs * kPPair;
 
-constexpr int kSmemRaw = kRawFloats * 4;        // 22,400
+// The raw buffer starts kRawShift floats into its 128-byte-aligned slab: the TMA source of a half-tile of a dense batch
+// sits at (5120 t - 200) * 4 = 96 mod 128 bytes, and a copy whose destination has the same offset inside a 128-byte line
+// is cheaper (tools/fused_ko.cu, -DWLM_RAW_SHIFT=0/8/16/24: 7,530 / 7,445 / 7,530 / 7,445 cycles per 64 frames; the two
+// sub-regions are 64 bytes apart modulo 128 for the bank layout, so only one of them can be co-aligned).
+#ifndef WLM_RAW_SHIFT
+#define WLM_RAW_SHIFT 24
+#endif
+constexpr int kRawShift = WLM_RAW_SHIFT;
+constexpr int kSmemRaw = kRawFloats * 4 + (kRawShift ? 128 : 0);        // 22,400 + 128
 constexpr int kSmemY = kYFloat2 * 8;
 constexpr int kSmemP = kPFloats * 4;
 constexpr int kSmemGroup = kSmemRaw + kSmemY + kSmemP;
@@ -234,7 +254,8 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "DONE_%=:\n"
         "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
-// same, acquiring at cluster scope: the data the barrier guards was written by other CTAs of the cluster
+// same, acquiring at cluster scope: the data the barrier guards was written by other CTAs of the cluster.  (The acquire
+// costs a CCTL.IVALL after the wait; a CTA-scope wait measured the same launch time, so the documented form stays.)
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n"
@@ -593,6 +614,36 @@ template <> __device__ __forceinline__ float from_out<__half>(__half v) { return
 // cost 6 % through the instruction cache): f(T*) is called with a.out as OutT*.
 template <class OutT, class F>
 __device__ __forceinline__ void with_out_type(const ClipArgs& a, F f) { f(static_cast<OutT*>(a.out)); }
+// One base pointer, immediate row offsets and one compare per row: left to the compiler, every row carried its own
+// predicated address computation (LDC + LEA + LEA.HI.X + two ISETP) -- the output pass was 180 instructions per half-tile.
+// base[ELEM_OFF] = v if q < lim: one compare and one predicated store with an immediate offset
+template <class T, int ELEM_OFF>
+__device__ __forceinline__ void store_row(T* base, float v, int lim, int q) {
+    if constexpr (sizeof(T) == 4) {
+        asm volatile("{\n.reg .pred p;\nsetp.lt.s32 p, %3, %4;\n@p st.global.f32 [%0+%1], %2;\n}"
+                     ::"l"(base), "n"(ELEM_OFF * 4), "f"(v), "r"(q), "r"(lim) : "memory");
+    } else {
+        const T t = to_out<T>(v);
+        asm volatile("{\n.reg .pred p;\nsetp.lt.s32 p, %3, %4;\n@p st.global.b16 [%0+%1], %2;\n}"
+                     ::"l"(base), "n"(ELEM_OFF * 2), "h"(*reinterpret_cast<const unsigned short*>(&t)), "r"(q), "r"(lim) : "memory");
+    }
+}
+
+// rows Q0 .. Q0+3 of one retained half-tile: (max(log10 p, floor_v) + 4) / 4  (TF-FE:155-161)
+template <class T, int Q0>
+__device__ __forceinline__ void output_block(T* of, const float (&r)[16], float floor_v, int lim) {
+    constexpr float kLog10_2 = 0.30102999566398120f;
+    float lg[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        lg[i] = fmaxf(lg2_approx(r[Q0 + i]) * kLog10_2, floor_v);
+        lg[i] = fmaf(lg[i], 0.25f, 1.0f);
+    }
+    store_row<T, (Q0 + 0) * kNFrames>(of, lg[0], lim, Q0 + 0);
+    store_row<T, (Q0 + 1) * kNFrames>(of, lg[1], lim, Q0 + 1);
+    store_row<T, (Q0 + 2) * kNFrames>(of, lg[2], lim, Q0 + 2);
+    store_row<T, (Q0 + 3) * kNFrames>(of, lg[3], lim, Q0 + 3);
+}
 
 // ---- the clip queue -----------------------------------------------------------------------------------------------
 // Clips are handed out dynamically: a worker (a cluster, or a CTA of the flat kernel) takes clip `worker` first (its
@@ -673,15 +724,31 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
     namespace cg = cooperative_groups;
     constexpr int kVC = FLAT ? kGroups : kVCluster;      // virtual CTAs (warp groups) that share a clip
     constexpr int kCl = FLAT ? 1 : kCluster;
-    extern __shared__ __align__(128) unsigned char smem[];
+    extern __shared__ __align__(128) unsigned char smem_sym[];
+#if WLM_OPAQUE_BASE
+    // The shared-memory base and the thread index as OPAQUE register values: left alone, the compiler re-derives every
+    // shared address from S2R SR_CgaCtaId and re-reads SR_TID.X wherever it is short of registers -- 13 S2R per warp and
+    // step, each ~50 cycles of latency on the path (3 % of the stall samples).
+    uint32_t smem_base_u32;
+    asm volatile("mov.b32 %0, %1;" : "=r"(smem_base_u32) : "r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem_sym))));
+    unsigned char* const smem = static_cast<unsigned char*>(__cvta_shared_to_generic(smem_base_u32));
+#else
+    unsigned char* const smem = smem_sym;
+#endif
     // this CTA is resident: once all of them are, the flat kernel (a programmatic dependent launch) may take the free SMs
     if constexpr (!FLAT) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#if WLM_OPAQUE_BASE
+    int tid;
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
+    const int lane = tid & 31;
+#else
     const int tid = threadIdx.x, lane = tid & 31;
+#endif
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler
     const int grp = warp / kGroupWarps, wg = warp % kGroupWarps;   // warp group and warp inside the group
 
     unsigned char* gbase = smem + grp * kSmemGroup;
-    float* raw = reinterpret_cast<float*>(gbase);
+    float* raw = reinterpret_cast<float*>(gbase) + kRawShift;
     float2* Y = reinterpret_cast<float2*>(gbase + kSmemRaw) + wg * kYWarpFloat2;      // this WARP's stage-1 output
     float* P = reinterpret_cast<float*>(gbase + kSmemRaw + kSmemY);
     unsigned char* misc = smem + kGroups * kSmemGroup;
@@ -835,6 +902,10 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
     bool have_max = false;                   // the pending clip's max has arrived (floor_v valid)
     float floor_v = 0.f;
 
+#ifdef WLM_WAITSTAT
+    long long ws_acc[5] = {0, 0, 0, 0, 0};
+    const long long ws_loop0 = clock64();
+#endif
     while (cvalid || pvalid || pend) {
         const bool do_tile = cvalid && cj < cn_my;
         const int ctile = vrank + cj * kVC;
@@ -870,7 +941,7 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
                     i_owe = false;
                 }
             }
-            if constexpr (!kKoRaw) mbar_wait(bar_raw, tnum & 1);
+            { WLM_WS_BEGIN(); if constexpr (!kKoRaw) mbar_wait(bar_raw, tnum & 1); WLM_WS_END(0); }
             tile_fixup(a, cc, ctile, raw, grp, tid & (kGroupThreads - 1));
             // This warp is done with raw once the 25-point DFTs have consumed its samples (the loads have then completed by
             // data dependence, so no fence holds the warp up between its loads and its arithmetic); the last of the 8
@@ -892,39 +963,31 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
         // ---- F: output of the clip that ended one step ago, ONE retained half-tile per step ----------------------
         // (the slot the mel stage below is about to overwrite: tcgen05.ld is 64 B/clk per SM, so a whole-clip pass by
         // all 16 warps at once stalls everything for ~4k cycles; spread over the next clip's steps it hides under the FFTs)
-        auto output_slot = [&](int j) {
-            constexpr float kLog10_2 = 0.30102999566398120f;
+        auto output_finish = [&](int j, const float (&r)[16]) {
             const int nf = kt.nf[wg];
-            float r[16];
-            tmem_wait_st();
-            tmem_ld_x16(twin + j * kTmemColsPerTile, r);
             const int f0 = (vrank + j * kVC) * kTile;
             const int64_t e0 = (static_cast<int64_t>(pend_b) * a.n_mels + kt.m0[wg]) * kNFrames + lane + f0;
-            const bool va = f0 + lane < kNFrames;
+            const int lim = f0 + lane < kNFrames ? nf : 0;       // rows this lane stores (frames past 3000 do not exist)
             with_out_type<OutT>(a, [&](auto* outp) {
                 using T = std::remove_pointer_t<decltype(outp)>;
                 T* of = outp + e0;
-                // rows in blocks of four: straight-line code inside a block, so four MUFU.LG2 chains overlap
-#pragma unroll
-                for (int q0 = 0; q0 < kMaxFiltersPerWarp; q0 += 4) {
-                    if (q0 < nf) {
-                        float lg[4];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            lg[i] = fmaxf(lg2_approx(r[q0 + i]) * kLog10_2, floor_v);
-                            lg[i] = fmaf(lg[i], 0.25f, 1.0f);   // (x+4)/4, TF-FE:161
-                        }
-#pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            if (va && q0 + i < nf) of[(q0 + i) * kNFrames] = to_out<T>(lg[i]);
-                    }
-                }
+                // rows in blocks of four (output_block): straight-line code inside a block, so four MUFU.LG2 chains overlap
+                if (0 < nf) output_block<T, 0>(of, r, floor_v, lim);
+                if (4 < nf) output_block<T, 4>(of, r, floor_v, lim);
+                if (8 < nf) output_block<T, 8>(of, r, floor_v, lim);
+                if (12 < nf) output_block<T, 12>(of, r, floor_v, lim);
             });
+        };
+        auto output_slot = [&](int j) {
+            float r[16];
+            tmem_wait_st();
+            tmem_ld_x16(twin + j * kTmemColsPerTile, r);
+            output_finish(j, r);
         };
         if (!FLAT && pend) {
             if (!have_max) {    // first step after the clip ended: the 12 maxima
                 const int fpar = fin_seq & 1;
-                mbar_wait_cluster(bar_max + fpar * 8, (fin_seq >> 1) & 1);
+                { WLM_WS_BEGIN(); mbar_wait_cluster(bar_max + fpar * 8, (fin_seq >> 1) & 1); WLM_WS_END(3); }
                 float pmax = lane < kVCluster ? clip_max[fpar * kVCluster + lane] : 0.f;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) pmax = fmaxf(pmax, __shfl_xor_sync(0xffffffffu, pmax, o));
@@ -946,7 +1009,10 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
                     }
                 });
             }
-            if (out_j < pend_n_my) { if constexpr (!kKoOut) output_slot(out_j); ++out_j; }
+            if (out_j < pend_n_my) {
+                if constexpr (!kKoOut) output_slot(out_j);
+                ++out_j;
+            }
             if (out_j >= pend_n_my) pend = false;
         }
         // ---- B: mel stage of the previous half-tile ---------------------------------------------------------
@@ -955,22 +1021,22 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
         const int cpar = fin_seq & 1;            // F has run: this is the parity of the clip ending now
         float wmax = 0.f;                        // this warp's max over the clip (valid when clip_ends)
         if (mel_tile) {
-            if constexpr (!kKoPfull) mbar_wait(bar_pfull, prev_tnum & 1);
+            { WLM_WS_BEGIN(); if constexpr (!kKoPfull) mbar_wait(bar_pfull, prev_tnum & 1); WLM_WS_END(1); }
             const uint32_t tcol = twin + pj * kTmemColsPerTile;
             float m1;
             if constexpr (FLAT) {
                 // no retention: (max(log10 p, -10) + 4) / 4 goes to HBM now, the max - 8 clamp follows when the clip is done
                 const int nf = kt.nf[wg];
                 const int64_t e0 = (static_cast<int64_t>(pb) * a.n_mels + kt.m0[wg]) * kNFrames + ptile * kTile + lane;
-                const bool va = ptile * kTile + lane < kNFrames;
+                const int lim = ptile * kTile + lane < kNFrames ? nf : 0;      // rows this lane stores
                 auto sink = [&](const float (&o)[kMaxFiltersPerWarp]) {
-                    constexpr float kLog10_2 = 0.30102999566398120f;
                     with_out_type<OutT>(a, [&](auto* outp) {
                         using T = std::remove_pointer_t<decltype(outp)>;
                         T* of = outp + e0;
-#pragma unroll
-                        for (int q = 0; q < kMaxFiltersPerWarp; ++q)
-                            if (q < nf && va) of[q * kNFrames] = to_out<T>(fmaf(fmaxf(lg2_approx(o[q]) * kLog10_2, -10.0f), 0.25f, 1.0f));
+                        if (0 < nf) output_block<T, 0>(of, o, -10.0f, lim);
+                        if (4 < nf) output_block<T, 4>(of, o, -10.0f, lim);
+                        if (8 < nf) output_block<T, 8>(of, o, -10.0f, lim);
+                        if (12 < nf) output_block<T, 12>(of, o, -10.0f, lim);
                     });
                 };
                 m1 = NMELS == 0 ? mel_stage(kt, P, wg, lane, sink) : mel_fixed<NMELS == 0 ? 80 : NMELS>(kt, P, wg, lane, sink);
@@ -1084,7 +1150,9 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
         if (do_tile) {
             stage2(Y, P, wg, lane, [&]() {
                 // the mel stage of the previous half-tile must have read P (all warps of the group)
+                WLM_WS_BEGIN();
                 if constexpr (!kKoPfree) if (tnum > 0) mbar_wait(bar_pfree, (tnum - 1) & 1);
+                WLM_WS_END(2);
             });
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_pfull);   // phase tnum
@@ -1111,6 +1179,11 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
             }
         }
     }
+#ifdef WLM_WAITSTAT
+    ws_acc[4] = clock64() - ws_loop0;
+    if (lane == 0 && a.gmax)
+        for (int k = 0; k < 5; ++k) a.gmax[(blockIdx.x * kWarps + warp) * 8 + k] = static_cast<float>(ws_acc[k]);
+#endif
     if constexpr (FLAT) {
         __syncthreads();
         // A programmatic dependent of the cluster kernel and the LAST kernel of the launch in the stream: it must not
