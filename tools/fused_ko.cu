@@ -77,6 +77,13 @@ int main(int argc, char** argv) {
     const double us = ms * 100.0, rounds = (double)B / maxc;
     printf("%s: B=%d clusters=%d: %.1f us per launch, %.2f us per round, %.0f cycles per 64 frames per SM (at 1.965 GHz)\n",
            argv[0], B, maxc, us, us / rounds, us / rounds / 8.0 * 1965.0);
+    {   // FNV-1a over the features of the last launch: builds that must agree bit for bit print the same value
+        std::vector<unsigned int> ho((size_t)B * M * 3000);
+        CK(cudaMemcpy(ho.data(), out, ho.size() * 4, cudaMemcpyDeviceToHost));
+        unsigned long long h64 = 1469598103934665603ull;
+        for (size_t i = 0; i < ho.size(); ++i) { h64 ^= ho[i]; h64 *= 1099511628211ull; }
+        printf("  features fnv64 %016llx\n", h64);
+    }
 #ifdef WLM_WAITSTAT
     {   // cycles per warp in each kind of wait, averaged over the warps of the launch (last launch)
         const int nw = (int)cfg.gridDim.x * 16;

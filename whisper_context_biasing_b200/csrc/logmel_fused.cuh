@@ -71,6 +71,10 @@ namespace fused {
 #endif
 constexpr bool kKoRaw = (WLM_KO & 1) != 0, kKoPfull = (WLM_KO & 2) != 0, kKoPfree = (WLM_KO & 4) != 0,
                kKoMel = (WLM_KO & 8) != 0, kKoOut = (WLM_KO & 16) != 0;
+// finer ones: 64 the copy moves 16 bytes per sub-region, 128 output stores predicated
+// off, 256 no tensor-memory read-back (the output pass works on stale registers), 512 no tensor-memory store
+constexpr bool kKoTinyTma = (WLM_KO & 64) != 0, kKoStg = (WLM_KO & 128) != 0,
+               kKoTld = (WLM_KO & 256) != 0, kKoTst = (WLM_KO & 512) != 0;
 
 // -DWLM_WAITSTAT (tools/fused_ko.cu only): every warp accumulates the cycles it spends in each kind of wait and leaves them
 // in a.gmax[(cta * 16 + warp) * 8 + {0 raw, 1 P full, 2 P free, 3 clip maxima, 4 whole loop}]
@@ -315,6 +319,7 @@ __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, float (&r)[16]) {
 // ---- clip / tile bookkeeping (all values group-uniform) -------------------------------------------
 struct ClipCtx {
     int b, len, n_act;     // clip index, valid samples (<= 480000), half-tiles that contain any real sample
+    int edge0;             // first half-tile that runs past the clip's samples (zero fill / reflection at the end)
     int64_t base;          // element offset of the clip in the PCM buffer
 };
 
@@ -327,6 +332,8 @@ __device__ __forceinline__ ClipCtx clip_ctx(const ClipArgs& a, int b) {
     c.len = max(0, min(len, kNSamples));
     // half-tile t starts at sample 5120 t - 200: active iff that is < len
     c.n_act = min(kTilesPerClip, (c.len + kNfft / 2 + kTile * kHop - 1) / (kTile * kHop));
+    // half-tile t covers samples [5120 t - 200, 5120 t + 5160): it runs past the clip iff 5120 t > len - 5160
+    c.edge0 = c.len >= kTileSamples - kNfft / 2 ? (c.len - (kTileSamples - kNfft / 2)) / (kTile * kHop) + 1 : 0;
     return c;
 }
 __device__ __forceinline__ int tile_s0(int tile) { return tile * (kTile * kHop) - kNfft / 2; }
@@ -335,6 +342,15 @@ __device__ __forceinline__ int tile_s0(int tile) { return tile * (kTile * kHop) 
 __device__ __forceinline__ void tile_issue_tma(const ClipArgs& a, const ClipCtx& c, int tile, float* raw, uint32_t bar) {
     const int s0 = tile_s0(tile);
     const int esz = a.pcm_format == WLM_PCM_I16 ? 2 : 4;
+    if (s0 >= 0 && s0 + kTileSamples <= c.len && !kKoTinyTma) {       // interior half-tile: two full sub-regions
+        const uint32_t bytes = static_cast<uint32_t>(kSubLen * esz);
+        mbar_expect_tx(bar, 2u * bytes);
+        const char* src = static_cast<const char*>(a.pcm) + (c.base + s0) * esz;
+        const uint32_t dst = smem_u32(raw) + (esz == 4 ? 0u : static_cast<uint32_t>(kSubLen) * 4u);
+        tma_bulk_g2s(dst, src, bytes, bar);
+        tma_bulk_g2s(dst + bytes, src + static_cast<int64_t>(kSubStep) * esz, bytes, bar);
+        return;
+    }
     const int gran = 16 / esz;
     const int len_up = min((c.len + gran - 1) / gran * gran, kNSamples);
     uint32_t total = 0;
@@ -345,6 +361,7 @@ __device__ __forceinline__ void tile_issue_tma(const ClipArgs& a, const ClipCtx&
         lo[r] = max(s_lo, 0);
         const int hi = min(s_lo + kSubLen, len_up);
         n[r] = max(hi - lo[r], 0);
+        if constexpr (kKoTinyTma) n[r] = min(n[r], 4);
         total += static_cast<uint32_t>(n[r]) * esz;
     }
     mbar_expect_tx(bar, total);
@@ -629,20 +646,45 @@ __device__ __forceinline__ void store_row(T* base, float v, int lim, int q) {
     }
 }
 
-// rows Q0 .. Q0+3 of one retained half-tile: (max(log10 p, floor_v) + 4) / 4  (TF-FE:155-161)
+// four rows at once when the lane stores all of them: one compare for the block
+template <class T, int ELEM_OFF>
+__device__ __forceinline__ void store_rows4(T* base, const float (&v)[4], int ok) {
+    if constexpr (sizeof(T) == 4) {
+        asm volatile("{\n.reg .pred p;\nsetp.ne.s32 p, %6, 0;\n@p st.global.f32 [%0+%1], %7;\n@p st.global.f32 [%0+%2], %8;\n"
+                     "@p st.global.f32 [%0+%3], %9;\n@p st.global.f32 [%0+%4], %10;\n}"
+                     ::"l"(base), "n"(ELEM_OFF * 4), "n"((ELEM_OFF + kNFrames) * 4), "n"((ELEM_OFF + 2 * kNFrames) * 4),
+                       "n"((ELEM_OFF + 3 * kNFrames) * 4), "n"(0), "r"(ok), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+    } else {
+        unsigned short h[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const T t = to_out<T>(v[i]);
+            h[i] = *reinterpret_cast<const unsigned short*>(&t);
+        }
+        asm volatile("{\n.reg .pred p;\nsetp.ne.s32 p, %6, 0;\n@p st.global.b16 [%0+%1], %7;\n@p st.global.b16 [%0+%2], %8;\n"
+                     "@p st.global.b16 [%0+%3], %9;\n@p st.global.b16 [%0+%4], %10;\n}"
+                     ::"l"(base), "n"(ELEM_OFF * 2), "n"((ELEM_OFF + kNFrames) * 2), "n"((ELEM_OFF + 2 * kNFrames) * 2),
+                       "n"((ELEM_OFF + 3 * kNFrames) * 2), "n"(0), "r"(ok), "h"(h[0]), "h"(h[1]), "h"(h[2]), "h"(h[3]) : "memory");
+    }
+}
+
+// rows Q0 .. Q0+3 of one retained half-tile: max((log10 p + 4) / 4, floor4) with floor4 = (floor + 4) / 4  (TF-FE:155-161;
+// the scale is folded into the logarithm's constant: lg2, one FFMA, one FMNMX per value).  `nf` (warp-uniform) = rows of
+// this warp, `lim` = rows this LANE stores (nf, or 0 for a frame past 3000).
 template <class T, int Q0>
-__device__ __forceinline__ void output_block(T* of, const float (&r)[16], float floor_v, int lim) {
-    constexpr float kLog10_2 = 0.30102999566398120f;
+__device__ __forceinline__ void output_block(T* of, const float (&r)[16], float floor4, int lim, int nf) {
+    constexpr float kLog10_2_4 = 0.30102999566398120f * 0.25f;
     float lg[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        lg[i] = fmaxf(lg2_approx(r[Q0 + i]) * kLog10_2, floor_v);
-        lg[i] = fmaf(lg[i], 0.25f, 1.0f);
+    for (int i = 0; i < 4; ++i) lg[i] = fmaxf(fmaf(lg2_approx(r[Q0 + i]), kLog10_2_4, 1.0f), floor4);
+    if (Q0 + 4 <= nf) {          // (warp-uniform) a full block: the lane stores all four rows or none
+        store_rows4<T, Q0 * kNFrames>(of, lg, lim);
+    } else {
+        store_row<T, (Q0 + 0) * kNFrames>(of, lg[0], lim, Q0 + 0);
+        store_row<T, (Q0 + 1) * kNFrames>(of, lg[1], lim, Q0 + 1);
+        store_row<T, (Q0 + 2) * kNFrames>(of, lg[2], lim, Q0 + 2);
+        store_row<T, (Q0 + 3) * kNFrames>(of, lg[3], lim, Q0 + 3);
     }
-    store_row<T, (Q0 + 0) * kNFrames>(of, lg[0], lim, Q0 + 0);
-    store_row<T, (Q0 + 1) * kNFrames>(of, lg[1], lim, Q0 + 1);
-    store_row<T, (Q0 + 2) * kNFrames>(of, lg[2], lim, Q0 + 2);
-    store_row<T, (Q0 + 3) * kNFrames>(of, lg[3], lim, Q0 + 3);
 }
 
 // ---- the clip queue -----------------------------------------------------------------------------------------------
@@ -745,6 +787,8 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
     const int tid = threadIdx.x, lane = tid & 31;
 #endif
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler
+    int tg;                                                   // thread index inside the warp group
+    asm volatile("mov.b32 %0, %1;" : "=r"(tg) : "r"(tid & (kGroupThreads - 1)));
     const int grp = warp / kGroupWarps, wg = warp % kGroupWarps;   // warp group and warp inside the group
 
     unsigned char* gbase = smem + grp * kSmemGroup;
@@ -839,11 +883,12 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
     int cb = first_clip, cj = 0, cn_my = 0;                         // clip, step inside the clip, half-tiles of mine in the clip
     bool cvalid = cb < a.B;
     ClipCtx cc;
-    cc.b = cb; cc.len = 0; cc.n_act = 0; cc.base = 0;
+    cc.b = cb; cc.len = 0; cc.n_act = 0; cc.base = 0; cc.edge0 = 0;
     if (cvalid) {
         cc = clip_ctx(a, cb);
         cn_my = my_tiles(cc.n_act);
     }
+    const int n_my_static = cn_my;
     bool pvalid = false, phas = false, plast = false;
     int pb = 0, pj = 0, ptile = 0, pn_my = 0, pn_act = 0;
     int clip_seq = 0;                        // (flat kernel) clips this warp has finished
@@ -886,21 +931,26 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
     // or whose own later work is needed to complete phase n+1, so the barrier is never more than one
     // phase ahead of a waiter.
     int fin_seq = 0;                         // clips whose output pass this warp has done; parity = slot of the exchange
-    int tnum = 0, prev_tnum = 0;             // ordinal of cur's / prev's half-tile among those of this group
+    int tnum = 0;                            // ordinal of cur's half-tile among those of this group (the previous step's is tnum - 1)
     bool i_owe = false;                      // (lane 0) this warp must issue the copy of the half-tile it is about to wait for
     bool q_pending = false;                  // (cluster leader) an atomic is in flight: its result is published one iteration later
     unsigned int q_val = 0;
     int q_ord = 0;
-    if ((tid & (kGroupThreads - 1)) == 0 && cvalid && !kKoRaw) {
+    if (tg == 0 && cvalid && !kKoRaw) {
         if (cn_my > 0) tile_issue_tma(a, cc, vrank, raw, bar_raw);
         else i_owe = !issue_next_tile(0, cc, 0, 0);
     }
+    // frames past 3000 do not exist: they are the last lanes of the clip's last half-tile
+    const bool tail_lane = lane >= kNFrames - (kTilesPerClip - 1) * kTile;
+    // ... as a step index: the step of this group whose half-tile is the clip's last one, for the lanes it matters to
+    const int tail_j = (tail_lane && (kTilesPerClip - 1 - vrank) % kVC == 0) ? (kTilesPerClip - 1 - vrank) / kVC : -1;
     float mx = 0.f;                          // running max of the mel power of the clip in flight (>= 0)
     bool pend = false;                       // an output pass is owed (max delivered, not yet waited for)
     int pend_b = 0, pend_n_my = 0;
+    int64_t pend_e0 = 0;                     // element index of (pending clip, this warp's first filter, frame = lane)
     int out_j = 0;                           // next retained half-tile of the pending clip to write out
-    bool have_max = false;                   // the pending clip's max has arrived (floor_v valid)
-    float floor_v = 0.f;
+    bool have_max = false;                   // the pending clip's max has arrived (floor4 valid)
+    float floor4 = 0.f;                      // (max(gmax - 8, -10) + 4) / 4: the clip's lowest feature value
 
 #ifdef WLM_WAITSTAT
     long long ws_acc[5] = {0, 0, 0, 0, 0};
@@ -942,7 +992,8 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
                 }
             }
             { WLM_WS_BEGIN(); if constexpr (!kKoRaw) mbar_wait(bar_raw, tnum & 1); WLM_WS_END(0); }
-            tile_fixup(a, cc, ctile, raw, grp, tid & (kGroupThreads - 1));
+            // interior half-tiles of float32 PCM need no patching (group-uniform condition: tile_fixup has group barriers)
+            if (a.pcm_format == WLM_PCM_I16 || ctile == 0 || ctile >= cc.edge0) tile_fixup(a, cc, ctile, raw, grp, tg);
             // This warp is done with raw once the 25-point DFTs have consumed its samples (the loads have then completed by
             // data dependence, so no fence holds the warp up between its loads and its arithmetic); the last of the 8
             // re-arms the TMA for the next half-tile, which is not needed before the next step.
@@ -950,7 +1001,8 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
                    [&]() {
                        __syncwarp();
                        if (lane == 0) {
-                           const uint32_t old = atomicAdd(raw_readers, 1u);
+                           uint32_t old;      // (plain atom: atomicAdd() brings its warp-aggregation code along)
+                           asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(raw_readers)) : "memory");
                            if (old == kGroupWarps - 1) {
                                *raw_readers = 0;
                                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -965,23 +1017,28 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
         // all 16 warps at once stalls everything for ~4k cycles; spread over the next clip's steps it hides under the FFTs)
         auto output_finish = [&](int j, const float (&r)[16]) {
             const int nf = kt.nf[wg];
-            const int f0 = (vrank + j * kVC) * kTile;
-            const int64_t e0 = (static_cast<int64_t>(pend_b) * a.n_mels + kt.m0[wg]) * kNFrames + lane + f0;
-            const int lim = f0 + lane < kNFrames ? nf : 0;       // rows this lane stores (frames past 3000 do not exist)
+            const int otile = vrank + j * kVC;
+            const int64_t e0 = pend_e0 + otile * kTile;
+            const int lim = (j != tail_j && !(kKoStg && a.B > 0)) ? nf : 0;       // rows this lane stores
             with_out_type<OutT>(a, [&](auto* outp) {
                 using T = std::remove_pointer_t<decltype(outp)>;
                 T* of = outp + e0;
                 // rows in blocks of four (output_block): straight-line code inside a block, so four MUFU.LG2 chains overlap
-                if (0 < nf) output_block<T, 0>(of, r, floor_v, lim);
-                if (4 < nf) output_block<T, 4>(of, r, floor_v, lim);
-                if (8 < nf) output_block<T, 8>(of, r, floor_v, lim);
-                if (12 < nf) output_block<T, 12>(of, r, floor_v, lim);
+                if (0 < nf) output_block<T, 0>(of, r, floor4, lim, nf);
+                if (4 < nf) output_block<T, 4>(of, r, floor4, lim, nf);
+                if (8 < nf) output_block<T, 8>(of, r, floor4, lim, nf);
+                if (12 < nf) output_block<T, 12>(of, r, floor4, lim, nf);
             });
         };
         auto output_slot = [&](int j) {
             float r[16];
-            tmem_wait_st();
-            tmem_ld_x16(twin + j * kTmemColsPerTile, r);
+            if constexpr (kKoTld) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) r[i] = floor4 + static_cast<float>(i + j);
+            } else {
+                tmem_wait_st();
+                tmem_ld_x16(twin + j * kTmemColsPerTile, r);
+            }
             output_finish(j, r);
         };
         if (!FLAT && pend) {
@@ -994,12 +1051,12 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
                 ++fin_seq;
                 have_max = true;
                 const float gmax = log10_floor(pmax);                 // TF-FE:157
-                floor_v = fmaxf(gmax - 8.0f, -10.0f);                 // TF-FE:158 (log-mel is never below -10)
-                if (vrank == 0 && (tid & (kGroupThreads - 1)) == 0 && a.gmax) a.gmax[pend_b] = gmax;
+                floor4 = (fmaxf(gmax - 8.0f, -10.0f) + 4.0f) * 0.25f;      // TF-FE:158,161 (log-mel is never below -10)
+                if (vrank == 0 && tg == 0 && a.gmax) a.gmax[pend_b] = gmax;
                 // half-tiles of mine that hold no real sample: log-mel is exactly -10 everywhere
-                const float silent = (floor_v + 4.0f) * 0.25f;
+                const float silent = floor4;
                 const int nf = kt.nf[wg];
-                const int64_t e0 = (static_cast<int64_t>(pend_b) * a.n_mels + kt.m0[wg]) * kNFrames + lane;
+                const int64_t e0 = pend_e0;
                 with_out_type<OutT>(a, [&](auto* outp) {
                     using T = std::remove_pointer_t<decltype(outp)>;
                     for (int tile = vrank + pend_n_my * kVCluster; tile < kTilesPerClip; tile += kVCluster) {
@@ -1021,31 +1078,34 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
         const int cpar = fin_seq & 1;            // F has run: this is the parity of the clip ending now
         float wmax = 0.f;                        // this warp's max over the clip (valid when clip_ends)
         if (mel_tile) {
-            { WLM_WS_BEGIN(); if constexpr (!kKoPfull) mbar_wait(bar_pfull, prev_tnum & 1); WLM_WS_END(1); }
+            { WLM_WS_BEGIN(); if constexpr (!kKoPfull) mbar_wait(bar_pfull, (tnum - 1) & 1); WLM_WS_END(1); }
             const uint32_t tcol = twin + pj * kTmemColsPerTile;
             float m1;
             if constexpr (FLAT) {
                 // no retention: (max(log10 p, -10) + 4) / 4 goes to HBM now, the max - 8 clamp follows when the clip is done
                 const int nf = kt.nf[wg];
                 const int64_t e0 = (static_cast<int64_t>(pb) * a.n_mels + kt.m0[wg]) * kNFrames + ptile * kTile + lane;
-                const int lim = ptile * kTile + lane < kNFrames ? nf : 0;      // rows this lane stores
+                const int lim = pj != tail_j ? nf : 0;      // rows this lane stores
                 auto sink = [&](const float (&o)[kMaxFiltersPerWarp]) {
                     with_out_type<OutT>(a, [&](auto* outp) {
                         using T = std::remove_pointer_t<decltype(outp)>;
                         T* of = outp + e0;
-                        if (0 < nf) output_block<T, 0>(of, o, -10.0f, lim);
-                        if (4 < nf) output_block<T, 4>(of, o, -10.0f, lim);
-                        if (8 < nf) output_block<T, 8>(of, o, -10.0f, lim);
-                        if (12 < nf) output_block<T, 12>(of, o, -10.0f, lim);
+                        if (0 < nf) output_block<T, 0>(of, o, -1.5f, lim, nf);      // (-10 + 4) / 4
+                        if (4 < nf) output_block<T, 4>(of, o, -1.5f, lim, nf);
+                        if (8 < nf) output_block<T, 8>(of, o, -1.5f, lim, nf);
+                        if (12 < nf) output_block<T, 12>(of, o, -1.5f, lim, nf);
                     });
                 };
                 m1 = NMELS == 0 ? mel_stage(kt, P, wg, lane, sink) : mel_fixed<NMELS == 0 ? 80 : NMELS>(kt, P, wg, lane, sink);
             } else {
-                auto sink = [&](const float (&o)[kMaxFiltersPerWarp]) { tmem_st_x16(tcol, o); };
+                auto sink = [&](const float (&o)[kMaxFiltersPerWarp]) {
+                    if constexpr (kKoTst) { if (o[3] == -1.0f) tmem_st_x16(tcol, o); }
+                    else tmem_st_x16(tcol, o);
+                };
                 if constexpr (kKoMel) m1 = P[lane];
                 else m1 = NMELS == 0 ? mel_stage(kt, P, wg, lane, sink) : mel_fixed<NMELS == 0 ? 80 : NMELS>(kt, P, wg, lane, sink);
             }
-            if (ptile * kTile + lane < kNFrames) mx = fmaxf(mx, m1);     // frames past 3000 do not exist
+            if (pj != tail_j) mx = fmaxf(mx, m1);
             if (clip_ends) {
                 wmax = mx;
 #pragma unroll
@@ -1053,7 +1113,7 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
                 mx = 0.f;
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_pfree);   // phase prev_tnum
+            if (lane == 0) mbar_arrive(bar_pfree);   // phase tnum - 1
         }
         // ---- D: the clip ended: warp max -> group max; the LAST warp of the group to get here delivers the group's
         // max to all 6 CTAs (remote store + remote mbarrier arrive).  Nobody waits; the peers get a whole step of
@@ -1143,8 +1203,10 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
             pend = true;
             have_max = false;
             out_j = 0;
-            pend_b = pb;
-            pend_n_my = pn_my;
+            // static assignment: every clip has the same length, and the clip that just ended is one stride back
+            pend_b = DYN ? pb : cb - n_static;
+            pend_e0 = (static_cast<int64_t>(pend_b) * a.n_mels + kt.m0[wg]) * kNFrames + lane;
+            pend_n_my = DYN ? pn_my : n_my_static;
         }
         // ---- C: stage 2 (every warp, on its own two frame pairs) ------------------------------------------
         if (do_tile) {
@@ -1160,8 +1222,9 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
         // this step becomes the previous one; advance to the next step of the stream
         const int steps = cn_my > 0 ? cn_my : 1;
         pvalid = cvalid; phas = do_tile; plast = cvalid && cj + 1 >= steps;
-        pb = cb; pj = cj; ptile = ctile; pn_my = cn_my; pn_act = cc.n_act;
-        prev_tnum = tnum;
+        pj = cj;
+        if constexpr (DYN || FLAT) { pb = cb; pn_my = cn_my; }
+        if constexpr (FLAT) { ptile = ctile; pn_act = cc.n_act; }
         if (do_tile) ++tnum;
         if (cvalid) {
             if (cj + 1 < steps) {
