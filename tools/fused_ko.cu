@@ -12,7 +12,10 @@ using namespace wlm;
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(1);} } while (0)
 
 int main(int argc, char** argv) {
-    const int B = argc > 1 ? atoi(argv[1]) : 242, M = 80;
+#ifndef KO_MELS
+#define KO_MELS 80
+#endif
+    const int B = argc > 1 ? atoi(argv[1]) : 242, M = KO_MELS;
     // a triangular bank with the structure of the 80-mel Whisper bank is not needed for timing: build the real one
     std::vector<float> dense(201 * M, 0.f);
     {   // Slaney bank (same formulas as feature_extraction.py), float32
@@ -43,7 +46,7 @@ int main(int argc, char** argv) {
     }
     static fused::Tables h;
     int variant = 0;
-    if (fused::build_tables(sp, M, &h, &variant) != 0 || variant != 80) { printf("table build failed (variant %d)\n", variant); return 1; }
+    if (fused::build_tables(sp, M, &h, &variant) != 0 || variant != KO_MELS) { printf("table build failed (variant %d)\n", variant); return 1; }
     fused::Tables* d;
     CK(cudaMalloc(&d, sizeof(h))); CK(cudaMemcpy(d, &h, sizeof(h), cudaMemcpyHostToDevice));
     float *pcm, *out, *gmax;
@@ -51,7 +54,7 @@ int main(int argc, char** argv) {
     std::vector<float> hp(480000);
     for (int i = 0; i < 480000; ++i) hp[i] = 0.1f * sinf(0.37f * i) + 0.05f * sinf(0.011f * i * i * 1e-3f);
     for (int b = 0; b < B; ++b) CK(cudaMemcpy(pcm + (size_t)b * 480000, hp.data(), 480000 * 4, cudaMemcpyHostToDevice));
-    auto fn = fused::logmel_cluster_kernel<80, false, float, false>;
+    auto fn = fused::logmel_cluster_kernel<KO_MELS, false, float, false>;
     CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::kSmemBytes));
     cudaLaunchConfig_t cfg; cudaLaunchAttribute at[1];
     memset(&cfg, 0, sizeof(cfg));

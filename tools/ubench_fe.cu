@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(kThreads, 1) fe_loop(const float* __restrict__
     if (warp < nwarps) {
 #pragma unroll 1
         for (int it = 0; it < ITERS; ++it) {
-            if (MODE != 2) stage1(raw, Y, wv, wg, lane, [&]() {}, [&]() {});
+            if (MODE != 2) stage1(stage1_base(raw, wg, lane), Y, wv, wg, lane, [&]() {}, [&]() {});
             __syncwarp();
             if (MODE != 1) stage2(Y, P, wg, lane, [&]() {});
             __syncwarp();

@@ -459,11 +459,14 @@ struct S1Load<25> {
     static __device__ __forceinline__ void run(uint32_t, uint32_t, uint32_t, const float (&)[25], V2 (&)[25]) {}
 };
 
+__device__ __forceinline__ uint32_t stage1_base(const float* raw, int wg, int lane) {
+    const int n1 = lane & 15, sub = lane >> 4;
+    return smem_u32(raw + sub * kSubLen + 2 * kHop * wg + 25 * n1);
+}
 template <class Loaded, class BeforeStore>
-__device__ __forceinline__ void stage1(const float* raw, float2* Y, const float (&wv)[25], int wg, int lane,
+__device__ __forceinline__ void stage1(uint32_t a0, float2* Y, const float (&wv)[25], int wg, int lane,
                                        Loaded loaded, BeforeStore before_store) {
     const int n1 = lane & 15, sub = lane >> 4;
-    const uint32_t a0 = smem_u32(raw + sub * kSubLen + 2 * kHop * wg + 25 * n1);
     V2 y[25];
     S1Load<0>::run(a0, a0 - 4u * kNfft, static_cast<uint32_t>(n1), wv, y);
     loaded();      // (fence inside: every LDS above has been performed)
@@ -780,8 +783,11 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
     // this CTA is resident: once all of them are, the flat kernel (a programmatic dependent launch) may take the free SMs
     if constexpr (!FLAT) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 #if WLM_OPAQUE_BASE
+    // (a special-register read is rematerialised by ptxas wherever it is short of a register, volatile or not; the result
+    // of a shuffle is not: the thread index goes through one)
     int tid;
     asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
+    tid = __shfl_sync(0xffffffffu, tid, tid & 31);
     const int lane = tid & 31;
 #else
     const int tid = threadIdx.x, lane = tid & 31;
@@ -789,7 +795,7 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler
     int tg;                                                   // thread index inside the warp group
     asm volatile("mov.b32 %0, %1;" : "=r"(tg) : "r"(tid & (kGroupThreads - 1)));
-    const int grp = warp / kGroupWarps, wg = warp % kGroupWarps;   // warp group and warp inside the group
+    const int grp = warp / kGroupWarps, wg = warp % kGroupWarps;   // warp group and warp inside the group (shift / mask instead measured 4 % SLOWER: a different register allocation)
 
     unsigned char* gbase = smem + grp * kSmemGroup;
     float* raw = reinterpret_cast<float*>(gbase) + kRawShift;
@@ -814,7 +820,15 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
 
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = FLAT ? 0 : static_cast<int>(cluster.block_rank());
-    const int vrank = rank * kGroups + grp;          // virtual CTA inside the clip
+    // virtual CTA inside the clip -- read back from shared memory for the same reason as the thread index: the cluster rank
+    // is a special register, and ptxas sees through a shuffle of a warp-uniform value
+    int vrank;
+    {
+        volatile int* pin = reinterpret_cast<volatile int*>(misc + 768) + warp;
+        if (lane == 0) *pin = rank * kGroups + grp;
+        __syncwarp();
+        vrank = *pin;
+    }
     // the worker's first clip is its index; the rest come from the queue (DYN) or follow at a stride of W workers
     const int worker = FLAT ? static_cast<int>(blockIdx.x) : static_cast<int>(blockIdx.x) / kCluster;
     const int n_static = FLAT ? static_cast<int>(gridDim.x) : static_cast<int>(gridDim.x) / kCluster;
@@ -862,7 +876,9 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
     const uint32_t twin = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) +
                           static_cast<uint32_t>((warp >> 2) * kTmemColsPerWarp);
 
-    // per-lane stage-1 constants
+    // per-lane stage-1 constants; the lane's first sample address is held in a register: re-derived, it is 15 instructions a step
+    // (through a shuffle with itself: ptxas re-derives anything it can trace back to special registers and parameters)
+    const uint32_t s1_base = __shfl_sync(0xffffffffu, stage1_base(raw, wg, lane), lane);
     const int n1 = lane & 15;
     float wv[25];
 #pragma unroll
@@ -997,14 +1013,13 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
             // This warp is done with raw once the 25-point DFTs have consumed its samples (the loads have then completed by
             // data dependence, so no fence holds the warp up between its loads and its arithmetic); the last of the 8
             // re-arms the TMA for the next half-tile, which is not needed before the next step.
-            stage1(raw, Y, wv, wg, lane, [&]() {},
+            stage1(s1_base, Y, wv, wg, lane, [&]() {},
                    [&]() {
                        __syncwarp();
                        if (lane == 0) {
-                           uint32_t old;      // (plain atom: atomicAdd() brings its warp-aggregation code along)
-                           asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(raw_readers)) : "memory");
+                           uint32_t old;      // (atom.inc wraps to 0 by itself; atom.add is turned into warp-aggregated code)
+                           asm volatile("atom.shared.inc.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(raw_readers)), "n"(kGroupWarps - 1) : "memory");
                            if (old == kGroupWarps - 1) {
-                               *raw_readers = 0;
                                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                                if constexpr (!kKoRaw) i_owe = !issue_next_tile(cord, cc, cn_my, cj);
                            }
