@@ -85,6 +85,10 @@ constexpr bool kKoTinyTma = (WLM_KO & 64) != 0, kKoStg = (WLM_KO & 128) != 0,
 #define WLM_WS_BEGIN()
 #define WLM_WS_END(k)
 #endif
+// suspend-time hint (ns) of the CTA-scope mbarrier waits; 0 = none
+#ifndef WLM_WAIT_HINT
+#define WLM_WAIT_HINT 0
+#endif
 #ifndef WLM_OPAQUE_BASE
 #define WLM_OPAQUE_BASE 1
 #endif
@@ -252,11 +256,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "{\n"
         ".reg .pred p;\n"
         "WAIT_%=:\n"
+#if WLM_WAIT_HINT
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+#else
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+#endif
         "@p bra DONE_%=;\n"
         "bra WAIT_%=;\n"
         "DONE_%=:\n"
-        "}\n" ::"r"(bar), "r"(parity) : "memory");
+        "}\n" ::"r"(bar), "r"(parity), "r"(WLM_WAIT_HINT) : "memory");
 }
 // same, acquiring at cluster scope: the data the barrier guards was written by other CTAs of the cluster.  (The acquire
 // costs a CCTL.IVALL after the wait; a CTA-scope wait measured the same launch time, so the documented form stays.)
