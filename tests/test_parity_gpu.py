@@ -183,6 +183,34 @@ def test_device_paths_agree_bitwise(fe):
     assert np.array_equal(alone[0], host[1])
 
 
+@pytest.mark.parametrize("L", [5160, 16000, 160000, 479996])
+def test_dense_short_rows_static_assignment(fe, L):
+    """A dense device batch [B, L] with L < 480000 runs on the STATIC kernels (every clip has the same number of half-tiles,
+    so they carry no per-clip state; warp groups that own no half-tile of such a clip take empty steps; the last half-tile is
+    patched with zeros).  It must equal, bit for bit, the same rows passed with explicit lengths (dynamic kernels, clip
+    queue) and with zero padding to 30 s, and match the oracle.  B = 75: more than three clips per cluster, flat share
+    included; 5160 samples = the half-tile boundary of the edge test."""
+    import torch
+
+    for m in (80, 128):
+        ex = fe[m]
+        g = torch.Generator(device="cuda").manual_seed(L)
+        B = 75
+        x = 0.1 * torch.randn(B, L, device=ex.device, generator=g)
+        a = ex.extract_device(x)                                                       # static
+        lens = torch.full((B,), L, dtype=torch.int32, device=ex.device)
+        b = ex.extract_device(x, lengths=lens)                                         # dynamic
+        assert torch.equal(a, b), (m, L)
+        full = torch.zeros(B, 480000, device=ex.device)
+        full[:, :L] = x
+        c = ex.extract_device(full)                                                    # static, 94 half-tiles
+        assert torch.equal(a, c), (m, L)
+        pick = [0, 21, 22, 43, 74]
+        ref = O.extract([x[i].cpu().numpy() for i in pick], m, "f64")
+        err = float(np.abs(a[pick].cpu().numpy() - ref).max())
+        assert err <= TOL, (m, L, err)
+
+
 def test_int16_ingest(fe):
     import torch
 
