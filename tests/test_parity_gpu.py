@@ -211,6 +211,35 @@ def test_dense_short_rows_static_assignment(fe, L):
         assert err <= TOL, (m, L, err)
 
 
+def test_back_to_back_launches_keep_stream_order(fe):
+    """The cluster kernel is a programmatic dependent launch of whatever precedes it in the stream: its prologue runs under
+    the tail of the previous kernel, and it waits for that kernel before it touches the caller's memory.  PCM written by an
+    earlier kernel of the same stream, the output buffer of the previous launch and the clip queue must therefore behave as
+    with ordinary stream order: a chain of (overwrite the PCM in place, extract into the same output, copy out) without any
+    synchronisation must give the features of each version."""
+    import torch
+
+    ex = fe[80]
+    g = torch.Generator(device="cuda").manual_seed(7)
+    for B, L, ragged in ((60, 480000, False), (60, 48000, True)):
+        versions = [0.1 * torch.randn(B, L, device=ex.device, generator=g) for _ in range(6)]
+        lens = torch.full((B,), L, dtype=torch.int32, device=ex.device) if ragged else None
+        want = []
+        for v in versions:
+            want.append(ex.extract_device(v, lengths=lens).clone())
+            torch.cuda.synchronize()
+        x = torch.empty(B, L, device=ex.device)
+        out = torch.empty(B, 80, 3000, device=ex.device)
+        got = []
+        for v in versions:                       # no synchronisation anywhere in this loop
+            x.copy_(v)                           # an ordinary kernel writes the PCM ...
+            ex.extract_device(x, lengths=lens, out=out)      # ... the launch right behind it must see it
+            got.append(out.clone())              # ... and the copy behind the launch must see all of its features
+        torch.cuda.synchronize()
+        for i, (a, b) in enumerate(zip(want, got)):
+            assert torch.equal(a, b), (B, L, ragged, i)
+
+
 def test_int16_ingest(fe):
     import torch
 

@@ -56,11 +56,14 @@ int main(int argc, char** argv) {
     for (int b = 0; b < B; ++b) CK(cudaMemcpy(pcm + (size_t)b * 480000, hp.data(), 480000 * 4, cudaMemcpyHostToDevice));
     auto fn = fused::logmel_cluster_kernel<KO_MELS, false, float, false>;
     CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::kSmemBytes));
-    cudaLaunchConfig_t cfg; cudaLaunchAttribute at[1];
+    cudaLaunchConfig_t cfg; cudaLaunchAttribute at[2];
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(fused::kCluster * 148); cfg.blockDim = dim3(fused::kThreads); cfg.dynamicSmemBytes = fused::kSmemBytes;
     at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = fused::kCluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
+#if WLM_PDL_CHAIN
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[1].val.programmaticStreamSerializationAllowed = 1; cfg.numAttrs = 2;
+#endif
     int maxc = 0;
     CK(cudaOccupancyMaxActiveClusters(&maxc, fn, &cfg));
     ClipArgs a;

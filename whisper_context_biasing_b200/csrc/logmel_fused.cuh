@@ -89,6 +89,10 @@ constexpr bool kKoTinyTma = (WLM_KO & 64) != 0, kKoStg = (WLM_KO & 128) != 0,
 #ifndef WLM_WAIT_HINT
 #define WLM_WAIT_HINT 0
 #endif
+// 1: the cluster kernel is itself a programmatic dependent launch (see the kernel's prologue)
+#ifndef WLM_PDL_CHAIN
+#define WLM_PDL_CHAIN 1
+#endif
 #ifndef WLM_OPAQUE_BASE
 #define WLM_OPAQUE_BASE 1
 #endif
@@ -788,8 +792,15 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
 #else
     unsigned char* const smem = smem_sym;
 #endif
+#if !WLM_PDL_CHAIN
     // this CTA is resident: once all of them are, the flat kernel (a programmatic dependent launch) may take the free SMs
     if constexpr (!FLAT) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#else
+    // (flat kernel) the NEXT launch's cluster kernel may be queued now: its CTAs become resident as the clusters of this
+    // launch exit and run their prologue; they wait for this launch to complete before they read or write anything of the
+    // caller's (griddepcontrol.wait below)
+    if constexpr (FLAT) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
 #if WLM_OPAQUE_BASE
     // (a special-register read is rematerialised by ptxas wherever it is short of a register, volatile or not; the result
     // of a shuffle is not: the thread index goes through one)
@@ -871,11 +882,6 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
         cluster.sync();     // (also a CTA barrier) every peer's mbarriers and queue ring exist before anyone writes them remotely
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         tmem_base = *tmem_slot;
-        if (leader) {                                            // (DYN) ordinals 1 and 2 of this cluster: one atomic
-            const unsigned int c = static_cast<unsigned int>(a.n_workers) + atomicAdd(&a.queue->next, 2u);
-            queue_put<false, kCluster>(clipq, 1, c < static_cast<unsigned int>(a.B) ? static_cast<int>(c) : kClipEnd);
-            queue_put<false, kCluster>(clipq, 2, c + 1 < static_cast<unsigned int>(a.B) ? static_cast<int>(c + 1) : kClipEnd);
-        }
     }
     // the imaginary part of slot 0 in the warp's Y: zeros, written once (stage 1 never stores there)
     Y[(lane >> 1) * kYN1 + kYLanes + (lane & 1)] = make_float2(0.f, 0.f);
@@ -891,6 +897,22 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
     float wv[25];
 #pragma unroll
     for (int t = 0; t < 25; ++t) wv[t] = win_lane[n1 * 25 + t];
+    if constexpr (!FLAT) {
+#if WLM_PDL_CHAIN
+        // Launched as a programmatic dependent of whatever precedes it in the stream (normally the previous wlm_logmel
+        // launch): the launch latency and the prologue above -- barrier and tensor-memory set-up, the cluster barrier, the
+        // window table -- overlap the tail of that kernel.  Nothing of the caller's has been touched so far (not the PCM,
+        // not the features, not the clip queue); from here on everything earlier in the stream has completed and is
+        // visible.  Only then may this launch's own dependent (the flat kernel, which reads PCM at once) start.
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+        if (leader) {                                            // (DYN) ordinals 1 and 2 of this cluster: one atomic
+            const unsigned int c = static_cast<unsigned int>(a.n_workers) + atomicAdd(&a.queue->next, 2u);
+            queue_put<false, kCluster>(clipq, 1, c < static_cast<unsigned int>(a.B) ? static_cast<int>(c) : kClipEnd);
+            queue_put<false, kCluster>(clipq, 2, c + 1 < static_cast<unsigned int>(a.B) ? static_cast<int>(c + 1) : kClipEnd);
+        }
+    }
 
     // The group's work is a stream of steps, one per half-tile it owns (a clip in which it owns no active
     // half-tile still contributes one empty step so that it takes part in that clip's max exchange).
@@ -1333,6 +1355,12 @@ inline void fill_launch_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* at,
     at[0].val.clusterDim.z = 1;
     cfg->attrs = at;
     cfg->numAttrs = 1;
+#if WLM_PDL_CHAIN
+    // the cluster kernel waits (griddepcontrol.wait) for its predecessor in the stream itself, after its prologue
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg->numAttrs = 2;
+#endif
 }
 
 inline cudaError_t configure(int variant, int* max_clusters) {
@@ -1344,7 +1372,7 @@ inline cudaError_t configure(int variant, int* max_clusters) {
             if (e != cudaSuccess) return e;
         }
     cudaLaunchConfig_t cfg;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     fill_launch_config(&cfg, at, 148, nullptr);
     int n = 0;
     e = cudaOccupancyMaxActiveClusters(&n, fn, &cfg);
@@ -1425,7 +1453,7 @@ inline cudaError_t launch(const ClipArgs& a0, const Tables* d_tables, const Tabl
         af.worker_base = nc;
     }
     cudaLaunchConfig_t cfg;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     fill_launch_config(&cfg, at, nc, st);
     *n_launches = 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, kernel_for(variant, false, a.out_format, dyn), a, h_tables.mel,
