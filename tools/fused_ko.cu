@@ -54,7 +54,10 @@ int main(int argc, char** argv) {
     std::vector<float> hp(480000);
     for (int i = 0; i < 480000; ++i) hp[i] = 0.1f * sinf(0.37f * i) + 0.05f * sinf(0.011f * i * i * 1e-3f);
     for (int b = 0; b < B; ++b) CK(cudaMemcpy(pcm + (size_t)b * 480000, hp.data(), 480000 * 4, cudaMemcpyHostToDevice));
-    auto fn = fused::logmel_cluster_kernel<KO_MELS, false, float, false>;
+    #ifndef KO_KERNEL_MELS
+#define KO_KERNEL_MELS KO_MELS
+#endif
+    auto fn = fused::logmel_cluster_kernel<KO_KERNEL_MELS, false, float, false>;   // 0 = the table-driven mel stage
     CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::kSmemBytes));
     cudaLaunchConfig_t cfg; cudaLaunchAttribute at[2];
     memset(&cfg, 0, sizeof(cfg));

@@ -354,7 +354,7 @@ __device__ __forceinline__ int tile_s0(int tile) { return tile * (kTile * kHop) 
 __device__ __forceinline__ void tile_issue_tma(const ClipArgs& a, const ClipCtx& c, int tile, float* raw, uint32_t bar) {
     const int s0 = tile_s0(tile);
     const int esz = a.pcm_format == WLM_PCM_I16 ? 2 : 4;
-    if (s0 >= 0 && s0 + kTileSamples <= c.len && !kKoTinyTma) {       // interior half-tile: two full sub-regions
+    if ((s0 >= 0 && s0 + kTileSamples <= c.len && !kKoTinyTma)) {       // interior half-tile: two full sub-regions
         const uint32_t bytes = static_cast<uint32_t>(kSubLen * esz);
         mbar_expect_tx(bar, 2u * bytes);
         const char* src = static_cast<const char*>(a.pcm) + (c.base + s0) * esz;
@@ -392,9 +392,12 @@ __device__ __forceinline__ void tile_issue_tma(const ClipArgs& a, const ClipCtx&
 // int16 -> float32 expansion in place (staging sits in the byte range of sub-region 1) + reflect /
 // zero-fill patching of every position outside [0, len).  Only edge tiles and int16 input pay.
 // Runs on the 256 threads of one group (tg = thread index inside the group).
-__device__ __forceinline__ void tile_fixup(const ClipArgs& a, const ClipCtx& c, int tile, float* raw, int grp, int tg) {
+// (scalars, not the argument structs: measured 1 % faster; as a __noinline__ function -- ~190 instructions an interior
+// half-tile never executes -- it measured 3 % SLOWER)
+__device__ __forceinline__ void tile_fixup(int pcm_format, int clip_len, int tile, float* raw, int grp, int tg) {
     const int s0 = tile_s0(tile);
-    if (a.pcm_format == WLM_PCM_I16) {
+    struct { int len; } c{clip_len};
+    if (pcm_format == WLM_PCM_I16) {
         const int16_t* st = reinterpret_cast<const int16_t*>(raw + kSubLen);
         constexpr float kScale = 1.0f / 32768.0f;
         constexpr int kPer = (kSubLen + kGroupThreads - 1) / kGroupThreads;
@@ -612,16 +615,21 @@ __device__ __forceinline__ float mel_fixed_warp(const KernelTables& kt, const fl
 
 template <int NMELS, class Sink>
 __device__ __forceinline__ float mel_fixed(const KernelTables& kt, const float* P, int wg, int lane, Sink sink) {
-    switch (wg) {
-        case 0: return mel_fixed_warp<NMELS, 0>(kt, P, lane, sink);
-        case 1: return mel_fixed_warp<NMELS, 1>(kt, P, lane, sink);
-        case 2: return mel_fixed_warp<NMELS, 2>(kt, P, lane, sink);
-        case 3: return mel_fixed_warp<NMELS, 3>(kt, P, lane, sink);
-        case 4: return mel_fixed_warp<NMELS, 4>(kt, P, lane, sink);
-        case 5: return mel_fixed_warp<NMELS, 5>(kt, P, lane, sink);
-        case 6: return mel_fixed_warp<NMELS, 6>(kt, P, lane, sink);
-        default: return mel_fixed_warp<NMELS, 7>(kt, P, lane, sink);
+    // a tree of direct branches, not a switch: that becomes an indirect branch through a jump table (BRX), measured 1 % slower
+    if (wg < 4) {
+        if (wg < 2) {
+            if (wg == 0) return mel_fixed_warp<NMELS, 0>(kt, P, lane, sink);
+            return mel_fixed_warp<NMELS, 1>(kt, P, lane, sink);
+        }
+        if (wg == 2) return mel_fixed_warp<NMELS, 2>(kt, P, lane, sink);
+        return mel_fixed_warp<NMELS, 3>(kt, P, lane, sink);
     }
+    if (wg < 6) {
+        if (wg == 4) return mel_fixed_warp<NMELS, 4>(kt, P, lane, sink);
+        return mel_fixed_warp<NMELS, 5>(kt, P, lane, sink);
+    }
+    if (wg == 6) return mel_fixed_warp<NMELS, 6>(kt, P, lane, sink);
+    return mel_fixed_warp<NMELS, 7>(kt, P, lane, sink);
 }
 
 // log10(max(p, 1e-10)) == max(log10 p, -10): exactly -10 for silence (TF-FE:155); p = 0 -> -inf -> -10
@@ -661,45 +669,83 @@ __device__ __forceinline__ void store_row(T* base, float v, int lim, int q) {
     }
 }
 
-// four rows at once when the lane stores all of them: one compare for the block
-template <class T, int ELEM_OFF>
-__device__ __forceinline__ void store_rows4(T* base, const float (&v)[4], int ok) {
+// N (1..4) consecutive rows at once when the lane stores all of them or none: one compare for the block
+template <class T, int ELEM_OFF, int N>
+__device__ __forceinline__ void store_rows(T* base, const float (&v)[4], int ok) {
+    static_assert(N >= 1 && N <= 4, "1..4 rows");
+    constexpr int kB = static_cast<int>(sizeof(T));
     if constexpr (sizeof(T) == 4) {
-        asm volatile("{\n.reg .pred p;\nsetp.ne.s32 p, %6, 0;\n@p st.global.f32 [%0+%1], %7;\n@p st.global.f32 [%0+%2], %8;\n"
-                     "@p st.global.f32 [%0+%3], %9;\n@p st.global.f32 [%0+%4], %10;\n}"
-                     ::"l"(base), "n"(ELEM_OFF * 4), "n"((ELEM_OFF + kNFrames) * 4), "n"((ELEM_OFF + 2 * kNFrames) * 4),
-                       "n"((ELEM_OFF + 3 * kNFrames) * 4), "n"(0), "r"(ok), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+        if constexpr (N == 4)
+            asm volatile("{\n.reg .pred p;\nsetp.ne.s32 p, %5, 0;\n@p st.global.f32 [%0+%1], %6;\n@p st.global.f32 [%0+%2], %7;\n"
+                         "@p st.global.f32 [%0+%3], %8;\n@p st.global.f32 [%0+%4], %9;\n}"
+                         ::"l"(base), "n"(ELEM_OFF * kB), "n"((ELEM_OFF + kNFrames) * kB), "n"((ELEM_OFF + 2 * kNFrames) * kB),
+                           "n"((ELEM_OFF + 3 * kNFrames) * kB), "r"(ok), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+        else if constexpr (N == 3)
+            asm volatile("{\n.reg .pred p;\nsetp.ne.s32 p, %4, 0;\n@p st.global.f32 [%0+%1], %5;\n@p st.global.f32 [%0+%2], %6;\n"
+                         "@p st.global.f32 [%0+%3], %7;\n}"
+                         ::"l"(base), "n"(ELEM_OFF * kB), "n"((ELEM_OFF + kNFrames) * kB), "n"((ELEM_OFF + 2 * kNFrames) * kB),
+                           "r"(ok), "f"(v[0]), "f"(v[1]), "f"(v[2]) : "memory");
+        else if constexpr (N == 2)
+            asm volatile("{\n.reg .pred p;\nsetp.ne.s32 p, %3, 0;\n@p st.global.f32 [%0+%1], %4;\n@p st.global.f32 [%0+%2], %5;\n}"
+                         ::"l"(base), "n"(ELEM_OFF * kB), "n"((ELEM_OFF + kNFrames) * kB), "r"(ok), "f"(v[0]), "f"(v[1]) : "memory");
+        else
+            asm volatile("{\n.reg .pred p;\nsetp.ne.s32 p, %2, 0;\n@p st.global.f32 [%0+%1], %3;\n}"
+                         ::"l"(base), "n"(ELEM_OFF * kB), "r"(ok), "f"(v[0]) : "memory");
     } else {
-        unsigned short h[4];
+        unsigned short h[4] = {0, 0, 0, 0};
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < N; ++i) {
             const T t = to_out<T>(v[i]);
             h[i] = *reinterpret_cast<const unsigned short*>(&t);
         }
-        asm volatile("{\n.reg .pred p;\nsetp.ne.s32 p, %6, 0;\n@p st.global.b16 [%0+%1], %7;\n@p st.global.b16 [%0+%2], %8;\n"
-                     "@p st.global.b16 [%0+%3], %9;\n@p st.global.b16 [%0+%4], %10;\n}"
-                     ::"l"(base), "n"(ELEM_OFF * 2), "n"((ELEM_OFF + kNFrames) * 2), "n"((ELEM_OFF + 2 * kNFrames) * 2),
-                       "n"((ELEM_OFF + 3 * kNFrames) * 2), "n"(0), "r"(ok), "h"(h[0]), "h"(h[1]), "h"(h[2]), "h"(h[3]) : "memory");
+        if constexpr (N == 4)
+            asm volatile("{\n.reg .pred p;\nsetp.ne.s32 p, %5, 0;\n@p st.global.b16 [%0+%1], %6;\n@p st.global.b16 [%0+%2], %7;\n"
+                         "@p st.global.b16 [%0+%3], %8;\n@p st.global.b16 [%0+%4], %9;\n}"
+                         ::"l"(base), "n"(ELEM_OFF * kB), "n"((ELEM_OFF + kNFrames) * kB), "n"((ELEM_OFF + 2 * kNFrames) * kB),
+                           "n"((ELEM_OFF + 3 * kNFrames) * kB), "r"(ok), "h"(h[0]), "h"(h[1]), "h"(h[2]), "h"(h[3]) : "memory");
+        else if constexpr (N == 3)
+            asm volatile("{\n.reg .pred p;\nsetp.ne.s32 p, %4, 0;\n@p st.global.b16 [%0+%1], %5;\n@p st.global.b16 [%0+%2], %6;\n"
+                         "@p st.global.b16 [%0+%3], %7;\n}"
+                         ::"l"(base), "n"(ELEM_OFF * kB), "n"((ELEM_OFF + kNFrames) * kB), "n"((ELEM_OFF + 2 * kNFrames) * kB),
+                           "r"(ok), "h"(h[0]), "h"(h[1]), "h"(h[2]) : "memory");
+        else if constexpr (N == 2)
+            asm volatile("{\n.reg .pred p;\nsetp.ne.s32 p, %3, 0;\n@p st.global.b16 [%0+%1], %4;\n@p st.global.b16 [%0+%2], %5;\n}"
+                         ::"l"(base), "n"(ELEM_OFF * kB), "n"((ELEM_OFF + kNFrames) * kB), "r"(ok), "h"(h[0]), "h"(h[1]) : "memory");
+        else
+            asm volatile("{\n.reg .pred p;\nsetp.ne.s32 p, %2, 0;\n@p st.global.b16 [%0+%1], %3;\n}"
+                         ::"l"(base), "n"(ELEM_OFF * kB), "r"(ok), "h"(h[0]) : "memory");
     }
 }
 
 // rows Q0 .. Q0+3 of one retained half-tile: max((log10 p + 4) / 4, floor4) with floor4 = (floor + 4) / 4  (TF-FE:155-161;
 // the scale is folded into the logarithm's constant: lg2, one FFMA, one FMNMX per value).  `nf` (warp-uniform) = rows of
-// this warp, `lim` = rows this LANE stores (nf, or 0 for a frame past 3000).
-template <class T, int Q0>
+// this warp, `lim` = rows this LANE stores (nf, or 0 for a frame past 3000).  NFC >= 0: nf is known at compile time (the
+// unrolled kernels), so is the length of the last block, and every block is stored under ONE compare.
+template <class T, int Q0, int NFC = -1>
 __device__ __forceinline__ void output_block(T* of, const float (&r)[16], float floor4, int lim, int nf) {
     constexpr float kLog10_2_4 = 0.30102999566398120f * 0.25f;
-    float lg[4];
+    constexpr int kRows = NFC < 0 ? 4 : (NFC - Q0 < 4 ? NFC - Q0 : 4);
+    float lg[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int i = 0; i < 4; ++i) lg[i] = fmaxf(fmaf(lg2_approx(r[Q0 + i]), kLog10_2_4, 1.0f), floor4);
-    if (Q0 + 4 <= nf) {          // (warp-uniform) a full block: the lane stores all four rows or none
-        store_rows4<T, Q0 * kNFrames>(of, lg, lim);
+    for (int i = 0; i < kRows; ++i) lg[i] = fmaxf(fmaf(lg2_approx(r[Q0 + i]), kLog10_2_4, 1.0f), floor4);
+    if constexpr (NFC >= 0) {
+        store_rows<T, Q0 * kNFrames, kRows>(of, lg, lim);
+    } else if (Q0 + 4 <= nf) {   // (warp-uniform) a full block: the lane stores all four rows or none
+        store_rows<T, Q0 * kNFrames, 4>(of, lg, lim);
     } else {
         store_row<T, (Q0 + 0) * kNFrames>(of, lg[0], lim, Q0 + 0);
         store_row<T, (Q0 + 1) * kNFrames>(of, lg[1], lim, Q0 + 1);
         store_row<T, (Q0 + 2) * kNFrames>(of, lg[2], lim, Q0 + 2);
         store_row<T, (Q0 + 3) * kNFrames>(of, lg[3], lim, Q0 + 3);
     }
+}
+// all rows of a warp whose run length is a compile-time constant
+template <class T, int NFC>
+__device__ __forceinline__ void output_rows(T* of, const float (&r)[16], float floor4, int lim) {
+    if constexpr (0 < NFC) output_block<T, 0, NFC>(of, r, floor4, lim, NFC);
+    if constexpr (4 < NFC) output_block<T, 4, NFC>(of, r, floor4, lim, NFC);
+    if constexpr (8 < NFC) output_block<T, 8, NFC>(of, r, floor4, lim, NFC);
+    if constexpr (12 < NFC) output_block<T, 12, NFC>(of, r, floor4, lim, NFC);
 }
 
 // ---- the clip queue -----------------------------------------------------------------------------------------------
@@ -816,6 +862,9 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
     asm volatile("mov.b32 %0, %1;" : "=r"(tg) : "r"(tid & (kGroupThreads - 1)));
     const int grp = warp / kGroupWarps, wg = warp % kGroupWarps;   // warp group and warp inside the group (shift / mask instead measured 4 % SLOWER: a different register allocation)
 
+    // this warp's run of filters: compile-time for the 128-mel bank (eight runs of 16), from the tables otherwise
+    auto warp_nf = [&]() -> int { if constexpr (NMELS == 128) return kMaxFiltersPerWarp; else return kt.nf[wg]; };
+    auto warp_m0 = [&]() -> int { if constexpr (NMELS == 128) return kMaxFiltersPerWarp * wg; else return kt.m0[wg]; };
     unsigned char* gbase = smem + grp * kSmemGroup;
     float* raw = reinterpret_cast<float*>(gbase) + kRawShift;
     float2* Y = reinterpret_cast<float2*>(gbase + kSmemRaw) + wg * kYWarpFloat2;      // this WARP's stage-1 output
@@ -1039,7 +1088,7 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
             }
             { WLM_WS_BEGIN(); if constexpr (!kKoRaw) mbar_wait(bar_raw, tnum & 1); WLM_WS_END(0); }
             // interior half-tiles of float32 PCM need no patching (group-uniform condition: tile_fixup has group barriers)
-            if (a.pcm_format == WLM_PCM_I16 || ctile == 0 || ctile >= cc.edge0) tile_fixup(a, cc, ctile, raw, grp, tg);
+            if ((a.pcm_format == WLM_PCM_I16 || ctile == 0 || ctile >= cc.edge0)) tile_fixup(a.pcm_format, cc.len, ctile, raw, grp, tg);
             // This warp is done with raw once the 25-point DFTs have consumed its samples (the loads have then completed by
             // data dependence, so no fence holds the warp up between its loads and its arithmetic); the last of the 8
             // re-arms the TMA for the next half-tile, which is not needed before the next step.
@@ -1061,7 +1110,7 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
         // (the slot the mel stage below is about to overwrite: tcgen05.ld is 64 B/clk per SM, so a whole-clip pass by
         // all 16 warps at once stalls everything for ~4k cycles; spread over the next clip's steps it hides under the FFTs)
         auto output_finish = [&](int j, const float (&r)[16]) {
-            const int nf = kt.nf[wg];
+            const int nf = warp_nf();
             const int otile = vrank + j * kVC;
             const int64_t e0 = pend_e0 + otile * kTile;
             const int lim = (j != tail_j && !(kKoStg && a.B > 0)) ? nf : 0;       // rows this lane stores
@@ -1069,10 +1118,15 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
                 using T = std::remove_pointer_t<decltype(outp)>;
                 T* of = outp + e0;
                 // rows in blocks of four (output_block): straight-line code inside a block, so four MUFU.LG2 chains overlap
-                if (0 < nf) output_block<T, 0>(of, r, floor4, lim, nf);
-                if (4 < nf) output_block<T, 4>(of, r, floor4, lim, nf);
-                if (8 < nf) output_block<T, 8>(of, r, floor4, lim, nf);
-                if (12 < nf) output_block<T, 12>(of, r, floor4, lim, nf);
+                if constexpr (NMELS == 128) {      // eight runs of 16: no run-length branches, one compare per block (-2 %)
+                    output_rows<T, kMaxFiltersPerWarp>(of, r, floor4, lim);       // (the same per warp for the 80-mel bank, behind
+                                                                                  // an 8-way dispatch: 500 more instructions, 4.5 % SLOWER)
+                } else {
+                    if (0 < nf) output_block<T, 0>(of, r, floor4, lim, nf);
+                    if (4 < nf) output_block<T, 4>(of, r, floor4, lim, nf);
+                    if (8 < nf) output_block<T, 8>(of, r, floor4, lim, nf);
+                    if (12 < nf) output_block<T, 12>(of, r, floor4, lim, nf);
+                }
             });
         };
         auto output_slot = [&](int j) {
@@ -1087,7 +1141,7 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
             output_finish(j, r);
         };
         if (!FLAT && pend) {
-            if (!have_max) {    // first step after the clip ended: the 12 maxima
+            if ((!have_max)) {    // first step after the clip ended: the 12 maxima
                 const int fpar = fin_seq & 1;
                 { WLM_WS_BEGIN(); mbar_wait_cluster(bar_max + fpar * 8, (fin_seq >> 1) & 1); WLM_WS_END(3); }
                 float pmax = lane < kVCluster ? clip_max[fpar * kVCluster + lane] : 0.f;
@@ -1100,7 +1154,7 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
                 if (vrank == 0 && tg == 0 && a.gmax) a.gmax[pend_b] = gmax;
                 // half-tiles of mine that hold no real sample: log-mel is exactly -10 everywhere
                 const float silent = floor4;
-                const int nf = kt.nf[wg];
+                const int nf = warp_nf();
                 const int64_t e0 = pend_e0;
                 with_out_type<OutT>(a, [&](auto* outp) {
                     using T = std::remove_pointer_t<decltype(outp)>;
@@ -1128,8 +1182,8 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
             float m1;
             if constexpr (FLAT) {
                 // no retention: (max(log10 p, -10) + 4) / 4 goes to HBM now, the max - 8 clamp follows when the clip is done
-                const int nf = kt.nf[wg];
-                const int64_t e0 = (static_cast<int64_t>(pb) * a.n_mels + kt.m0[wg]) * kNFrames + ptile * kTile + lane;
+                const int nf = warp_nf();
+                const int64_t e0 = (static_cast<int64_t>(pb) * a.n_mels + warp_m0()) * kNFrames + ptile * kTile + lane;
                 const int lim = pj != tail_j ? nf : 0;      // rows this lane stores
                 auto sink = [&](const float (&o)[kMaxFiltersPerWarp]) {
                     with_out_type<OutT>(a, [&](auto* outp) {
@@ -1163,7 +1217,7 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
         // ---- D: the clip ended: warp max -> group max; the LAST warp of the group to get here delivers the group's
         // max to all 6 CTAs (remote store + remote mbarrier arrive).  Nobody waits; the peers get a whole step of
         // slack before anyone needs the result (F, next step).
-        if (FLAT && clip_ends) {
+        if (FLAT && (clip_ends)) {
             // The CTA's 16 warps meet (once per clip), take the clip's max and clamp the clip's features in place:
             // they were written moments ago and come back from L2.  flat_max is a ring of three so that the slot of the
             // clip after next can be cleared here without racing with anybody (its last readers arrived above, its next
@@ -1217,7 +1271,7 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
             });
             ++clip_seq;
         }
-        if (!FLAT && clip_ends) {
+        if (!FLAT && (clip_ends)) {
             while (pend) {      // (only when this clip had fewer half-tiles than the one before it: finish that one first)
                 if (out_j < pend_n_my) output_slot(out_j++);
                 if (out_j >= pend_n_my) pend = false;
@@ -1250,7 +1304,7 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
             out_j = 0;
             // static assignment: every clip has the same length, and the clip that just ended is one stride back
             pend_b = DYN ? pb : cb - n_static;
-            pend_e0 = (static_cast<int64_t>(pend_b) * a.n_mels + kt.m0[wg]) * kNFrames + lane;
+            pend_e0 = (static_cast<int64_t>(pend_b) * a.n_mels + warp_m0()) * kNFrames + lane;
             pend_n_my = DYN ? pn_my : n_my_static;
         }
         // ---- C: stage 2 (every warp, on its own two frame pairs) ------------------------------------------
