@@ -348,6 +348,13 @@ __device__ __forceinline__ ClipCtx clip_ctx(const ClipArgs& a, int b) {
     c.edge0 = c.len >= kTileSamples - kNfft / 2 ? (c.len - (kTileSamples - kNfft / 2)) / (kTile * kHop) + 1 : 0;
     return c;
 }
+// the same clip context for another clip of a STATIC launch: every clip has the same length, only the position differs
+__device__ __forceinline__ ClipCtx clip_ctx_like(const ClipArgs& a, const ClipCtx& c0, int b) {
+    ClipCtx c = c0;
+    c.b = b;
+    c.base = a.offsets ? a.offsets[b] : static_cast<int64_t>(b) * a.row_stride;
+    return c;
+}
 __device__ __forceinline__ int tile_s0(int tile) { return tile * (kTile * kHop) - kNfft / 2; }
 
 // issued by one thread: both sub-regions of the half-tile, valid sample range only
@@ -421,6 +428,7 @@ __device__ __forceinline__ void tile_fixup(int pcm_format, int clip_len, int til
     // Only the positions outside [0, len) are touched (a scan of the whole buffer cost ~8k cycles on the first
     // half-tile of every clip, and the other 11 virtual CTAs of the cluster wait for that one at the clip's end).
     if (s0 < 0) {   // first half-tile: s = idx - 200 < 0 reflects to sample 200 - idx (torch.stft center=True, TF-FE:149)
+#pragma unroll 1
         for (int idx = tg; idx < -s0; idx += kGroupThreads) {
             const int sr = -(s0 + idx);
             raw[idx] = sr < c.len ? raw[sr - s0] : 0.f;        // (sr - s0 <= 400 < kSubLen: same sub-region)
@@ -430,6 +438,7 @@ __device__ __forceinline__ void tile_fixup(int pcm_format, int clip_len, int til
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
             const int s_lo = s0 + r * kSubStep;
+#pragma unroll 1
             for (int i = max(c.len - s_lo, 0) + tg; i < kSubLen; i += kGroupThreads) {
                 const int s = s_lo + i;
                 float v = 0.f;
@@ -1007,7 +1016,7 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
                 const int nb = c0.b + n_static;
                 tt = vrank;
                 if (nb < a.B && c0.n_act > vrank) {
-                    ct = clip_ctx(a, nb);
+                    ct = clip_ctx_like(a, c0, nb);
                     have = true;
                 }
             }
@@ -1169,6 +1178,7 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
                 const int64_t e0 = pend_e0;
                 with_out_type<OutT>(a, [&](auto* outp) {
                     using T = std::remove_pointer_t<decltype(outp)>;
+                    // (left to the compiler's unrolling: ragged batches of short clips spend real time here)
                     for (int tile = vrank + pend_n_my * kVCluster; tile < kTilesPerClip; tile += kVCluster) {
                         T* of = outp + e0 + tile * kTile;
                         if (tile * kTile + lane < kNFrames)
@@ -1302,6 +1312,7 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
                     // whole group was then waiting for).  Every CTA's group 0 posts the expectation of 12 x 4 bytes.
                     const uint32_t slot_l = smem_u32(clip_max + cpar * kVCluster + vrank), bar_l = bar_max + cpar * 8;
                     if (grp == 0) mbar_expect_tx(bar_l, 4u * kVCluster);
+#pragma unroll 1      /* once per clip and group: kept a loop, the body of the step loop is short of instruction cache */
                     for (int r = 0; r < kCluster; ++r) {
                         uint32_t slot_r, bar_r;
                         asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(slot_r) : "r"(slot_l), "r"(r));
@@ -1347,8 +1358,13 @@ logmel_cluster_kernel(const ClipArgs a, const __grid_constant__ KernelTables kt,
                 cn_my = 0;
                 cvalid = cb < a.B;
                 if (cvalid) {
-                    cc = clip_ctx(a, cb);
-                    cn_my = my_tiles(cc.n_act);
+                    if constexpr (DYN) {
+                        cc = clip_ctx(a, cb);
+                        cn_my = my_tiles(cc.n_act);
+                    } else {
+                        cc = clip_ctx_like(a, cc, cb);
+                        cn_my = n_my_static;
+                    }
                 }
             }
         }
