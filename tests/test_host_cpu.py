@@ -78,3 +78,24 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in txt.replace("no oracle", ""), f"{f} mentions the oracle"
+
+
+def test_committed_profiles_belong_to_the_shipped_kernel_sources():
+    """bench.py prints `roofline.traffic` only when profiles/<tag>_summary.json was captured from a build of exactly the
+    kernel sources in the tree (tools/ncu_summary.py records their sha).  The newest C2 and C3 summaries must match, or
+    the bench line would silently lose its ncu evidence."""
+    import importlib.util
+    import json
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("_wlm_build_t", os.path.join(root, "whisper_context_biasing_b200", "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    sha = mod.kernel_sources_sha()
+    pdir = os.path.join(root, "profiles")
+    for suffix in ("_c2_80mel_summary.json", "_c3_128mel_summary.json"):
+        cands = sorted(f for f in os.listdir(pdir) if f.endswith(suffix))
+        assert cands, suffix
+        doc = json.load(open(os.path.join(pdir, cands[-1])))
+        assert doc.get("kernel_sources_sha") == sha, (cands[-1], doc.get("kernel_sources_sha"), sha)
+        assert doc["kernels"] if "kernels" in doc else True
